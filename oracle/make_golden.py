@@ -1,0 +1,197 @@
+"""Generate golden vectors by EXECUTING the unmodified reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+Writes small ``tests/golden/*.pt`` fixtures (committed).  Each fixture holds the initial ``state_dict``s, every
+host-side random draw the reference made (latents, second latents + mixing cut-offs, images, per-layer noise) and
+the reference's outputs, so that both the oracle and the CUDA engine can be replayed against it without the
+reference being importable.  Test infrastructure; never imported by the product path.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("SG_REFERENCE", "/root/reference")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(1, HERE)
+
+from models.GAN import StyleGAN  # noqa: E402  (the reference)
+from models.CustomLayers import NoiseLayer  # noqa: E402
+import stylegan_oracle as O  # noqa: E402
+
+
+def seed_all(s):
+    torch.manual_seed(s)
+    random.seed(s)
+    np.random.seed(s)
+
+
+def build_reference(arch: O.Arch, loss="logistic", use_ema=True):
+    gk = arch.g_kwargs()
+    dk = arch.d_kwargs()
+    for k in ("resolution", "num_channels", "structure"):
+        gk.pop(k, None)
+        dk.pop(k, None)
+    latent = gk.pop("latent_size")
+    gk["latent_size"] = latent
+    opt = dict(learning_rate=0.003, beta_1=0.0, beta_2=0.99, eps=1e-8)   # config.py:79-92 (beta_1 as float)
+    return StyleGAN(structure=arch.structure, resolution=arch.resolution, num_channels=arch.num_channels,
+                    latent_size=latent, g_args=gk, d_args=dk, g_opt_args=opt, d_opt_args=dict(opt),
+                    loss=loss, use_ema=use_ema, ema_decay=0.999, device=torch.device("cpu"))
+
+
+def randomize_zero_inits(sg):
+    """Noise weights and all biases start at zero in the reference; perturb them so those paths are exercised."""
+    with torch.no_grad():
+        for net in (sg.gen, sg.dis):
+            for n, p in net.named_parameters():
+                if n.endswith("noise.weight"):
+                    p.copy_(torch.randn_like(p))
+                elif n.endswith(".bias") and "init_block.bias" not in n:
+                    p.copy_(0.1 * torch.randn_like(p))
+        if sg.use_ema:
+            sg.gen_shadow.load_state_dict(sg.gen.state_dict())
+
+
+def set_noise(gen, batch):
+    """Fix every NoiseLayer's noise (CustomLayers.py:194-198).  Returns the list in module order."""
+    noises = []
+    res = 4
+    layers = [m for m in gen.g_synthesis.modules() if isinstance(m, NoiseLayer)]
+    for i, m in enumerate(layers):
+        r = 4 * 2 ** (i // 2)
+        n = torch.randn(batch, 1, r, r)
+        m.noise = n
+        noises.append(n)
+    return noises
+
+
+def clone_sd(sd):
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def record_mixing(arch, z_shape, depth):
+    """Peek the host RNG draws the next training-mode Generator.forward will make, then rewind."""
+    ts, ps = torch.get_rng_state(), random.getstate()
+    z2, cutoff = O.draw_mixing(arch, z_shape, depth)
+    torch.set_rng_state(ts)
+    random.setstate(ps)
+    return z2, cutoff
+
+
+def golden_trajectory(name, arch, batch, schedule, seed=0, outdir=None):
+    """`schedule` = list of (depth, alpha) G+D steps."""
+    seed_all(seed)
+    sg = build_reference(arch)
+    randomize_zero_inits(sg)
+    sg.gen.train(); sg.dis.train(); sg.gen_shadow.train()
+    noises = set_noise(sg.gen, batch)
+    fx = dict(arch=arch.__dict__.copy(), batch=batch, schedule=schedule,
+              g_init=clone_sd(sg.gen.state_dict()), d_init=clone_sd(sg.dis.state_dict()),
+              noises=noises, steps=[])
+    for depth, alpha in schedule:
+        images = torch.randn(batch, arch.num_channels, arch.resolution, arch.resolution)
+        z = torch.randn(batch, arch.latent_size)
+        mix_d = record_mixing(arch, z.shape, depth)
+        d_loss = sg.optimize_discriminator(z, images, depth, alpha)
+        mix_g = record_mixing(arch, z.shape, depth)
+        g_loss = sg.optimize_generator(z, images, depth, alpha)
+        fx["steps"].append(dict(images=images, z=z, mix_d=mix_d, mix_g=mix_g, d_loss=d_loss, g_loss=g_loss))
+    fx["g_final"] = clone_sd(sg.gen.state_dict())
+    fx["d_final"] = clone_sd(sg.dis.state_dict())
+    fx["shadow_final"] = clone_sd(sg.gen_shadow.state_dict())
+    g_names = [n for n, _ in sg.gen.named_parameters()]
+    d_names = [n for n, _ in sg.dis.named_parameters()]
+    gs, ds = sg.gen_optim.state_dict()["state"], sg.dis_optim.state_dict()["state"]
+    fx["g_exp_avg_sq"] = {g_names[i]: s["exp_avg_sq"].clone() for i, s in gs.items()}
+    fx["d_exp_avg_sq"] = {d_names[i]: s["exp_avg_sq"].clone() for i, s in ds.items()}
+    fx["g_adam_step"] = {g_names[i]: int(s["step"]) for i, s in gs.items()}
+    fx["d_adam_step"] = {d_names[i]: int(s["step"]) for i, s in ds.items()}
+    out = os.path.join(outdir or os.path.join(ROOT, "tests", "golden"), name + ".pt")
+    torch.save(fx, out)
+    print(name, "->", out, "%.1f KB" % (os.path.getsize(out) / 1024),
+          "losses", [(round(s["d_loss"], 4), round(s["g_loss"], 4)) for s in fx["steps"]][:3], "...")
+
+
+def golden_forward_backward(name, arch, batch, depth, alpha, seed=1):
+    """Single-point forward/backward/R1 fixture (gradients kept as per-tensor norms + a few full tensors)."""
+    seed_all(seed)
+    sg = build_reference(arch)
+    randomize_zero_inits(sg)
+    sg.gen.train(); sg.dis.train()
+    noises = set_noise(sg.gen, batch)
+    z = torch.randn(batch, arch.latent_size)
+    res = 2 ** (depth + 2)
+    real = torch.randn(batch, arch.num_channels, res, res)
+    mix = record_mixing(arch, z.shape, depth)
+    g_init = clone_sd(sg.gen.state_dict())
+    d_init = clone_sd(sg.dis.state_dict())
+    fake = sg.gen(z, depth, alpha)
+    avg_after = sg.gen.truncation.avg_latent.clone() if sg.gen.truncation is not None else None
+    logits_fake = sg.dis(fake, depth, alpha)
+    logits_real = sg.dis(real, depth, alpha)
+    r1 = sg.loss.R1Penalty(real, depth, alpha)
+    d_loss = sg.loss.dis_loss(real, fake.detach(), depth, alpha)
+    d_params = [p for p in sg.dis.parameters()]
+    d_grads = torch.autograd.grad(d_loss, d_params, allow_unused=True)
+    g_loss = sg.loss.gen_loss(None, fake, depth, alpha)
+    g_params = [p for p in sg.gen.parameters()]
+    g_grads = torch.autograd.grad(g_loss, g_params, allow_unused=True)
+    gn = [n for n, _ in sg.gen.named_parameters()]
+    dn = [n for n, _ in sg.dis.named_parameters()]
+
+    def pack(names, grads):
+        out = {}
+        for n, g in zip(names, grads):
+            if g is None:
+                continue
+            out[n] = dict(norm=float(g.norm()), full=g.clone() if g.numel() <= 4096 else None,
+                          head=g.flatten()[:64].clone())
+        return out
+    fx = dict(arch=arch.__dict__.copy(), batch=batch, depth=depth, alpha=alpha, g_init=g_init, d_init=d_init,
+              noises=noises[:2 * (depth + 1)], z=z, real=real, mix=mix, fake=fake.detach(), avg_after=avg_after,
+              logits_fake=logits_fake.detach(), logits_real=logits_real.detach(), r1=float(r1),
+              d_loss=float(d_loss), g_loss=float(g_loss), d_grads=pack(dn, d_grads), g_grads=pack(gn, g_grads))
+    out = os.path.join(ROOT, "tests", "golden", name + ".pt")
+    torch.save(fx, out)
+    print(name, "->", out, "%.1f KB" % (os.path.getsize(out) / 1024), "d_loss %.5f g_loss %.5f r1 %.5f" %
+          (fx["d_loss"], fx["g_loss"], fx["r1"]))
+
+
+def live_full_width(outdir):
+    """BASELINE config 1 at the reference's real channel widths (too large to commit): resolution-128 config,
+    depth 1 (8x8) and depth 2 (16x16), batch 4.  Used by tests/test_oracle_vs_reference.py in the build container."""
+    full = O.Arch(128)
+    golden_trajectory("live_full128", full, batch=4, schedule=[(1, 0.5), (1, 0.75), (2, 0.5), (2, 1.0)],
+                      outdir=outdir)
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--live":
+        os.makedirs(sys.argv[2], exist_ok=True)
+        return live_full_width(sys.argv[2])
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    # low-resolution (unfused up/down) trajectory: 10 G+D steps, BASELINE config 1 in miniature
+    tiny16 = O.Arch(16, latent_size=32, dlatent_size=512, mapping_fmaps=32, mapping_layers=4, fmap_base=128,
+                    fmap_max=32)   # dlatent must stay 512: the reference does not forward it to GSynthesis (GAN.py:244)
+    golden_trajectory("traj_tiny16", tiny16, batch=4,
+                      schedule=[(1, 0.25), (1, 0.5), (1, 1.0)] + [(2, 0.1 * i) for i in range(1, 8)])
+    # depth 0 (no fade branch) forward/backward
+    golden_forward_backward("fb_tiny16_d0", tiny16, batch=4, depth=0, alpha=1.0)
+    # fused up-conv (64->128) and fused down-conv (128->64): resolution 128 with thin channels
+    tiny128 = O.Arch(128, latent_size=32, dlatent_size=512, mapping_fmaps=32, mapping_layers=2, fmap_base=256,
+                     fmap_max=16)
+    golden_forward_backward("fb_tiny128_d5", tiny128, batch=4, depth=5, alpha=0.5)
+    golden_forward_backward("fb_tiny128_d4", tiny128, batch=4, depth=4, alpha=0.3, seed=2)
+
+
+if __name__ == "__main__":
+    main()

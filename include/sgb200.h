@@ -1,0 +1,153 @@
+/* sgb200.h -- C ABI of libsgb200.so, the B200 (sm_100a) StyleGAN training-step kernels.
+ *
+ * The reference (huangzh13/StyleGAN.pytorch) has no FFI: its seam is the Python class API of models/*.py and all
+ * arithmetic is delegated to torch.  Each entry point below replaces the torch call sites named
+ * in its comment (paths relative to the reference root).  Conventions:
+ *   - plain device pointers + sizes, no torch types; the caller owns every buffer (outputs, workspaces);
+ *   - activations are NHWC ("channels-last") contiguous; `dtype` 0 = float32, 1 = bfloat16 (fp32 accumulation);
+ *     parameters, gradients of parameters, statistics and images (NCHW) are always float32;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never allocates, never synchronises;
+ *   - returns 0 on success, otherwise a cudaError_t value or >=1000 for argument errors; sg_last_error() describes it.
+ */
+#ifndef SGB200_H
+#define SGB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB200_ABI_VERSION 1
+
+/* Tap-table geometry shared by forward, dgrad and wgrad of every dense convolution (see csrc/sg_conv_generic.cu):
+ *   out[n, qy*os+py, qx*os+px, :] = sum_t in[n, qy*is+dy[ph][t], qx*is+dx[ph][t], :] * E[ph][t]   (ph = 2*py+px) */
+typedef struct SgConvGeom {
+  int32_t N, Hq, Wq;
+  int32_t Hin, Win, Cin;
+  int32_t Hout, Wout, Cout;
+  int32_t in_stride, out_stride;
+  int32_t nphase, ntaps;
+  int8_t dy[4][16];
+  int8_t dx[4][16];
+} SgConvGeom;
+
+/* One row of the multi-tensor optimizer table (device memory).  Pointers are device addresses stored as int64. */
+typedef struct SgTensorEntry {
+  int64_t p, g, m, v, ema, step; /* ema may be 0; step -> float32 scalar (torch.optim.Adam state['step']) */
+  int64_t n;                     /* elements */
+  int64_t chunk0;                /* first chunk index of this tensor (chunks of sg_chunk_elems()) */
+} SgTensorEntry;
+
+const char* sg_last_error(void);
+int sg_abi_version(void);
+int sg_geom_size(void);
+int sg_entry_size(void);
+
+/* ---- dense convolutions: EqualizedConv2d.forward, models/CustomLayers.py:137-180 (F.conv2d :163,:171,:173,
+ *      F.conv_transpose2d :151) and their autograd adjoints ------------------------------------------------------- */
+/* E[ph][t][a][b] = scale * sum_j coef[ph*ntaps+t][j] * W[co][ci][j]; (a,b) = transpose ? (co,ci) : (ci,co).
+ * Replaces `self.weight * self.w_mul` (:171) and the 4x4 kernel merges (:146-150, :159-162). */
+int sg_wprep_fwd(const float* W, void* E, int dtype, int Cout, int Cin, int KK, int npt, const float* coef,
+                 float scale, int transpose, void* stream);
+/* dW = scale * coef^T . sum_splits(partial)  -- adjoint of sg_wprep_fwd applied to the wgrad partials. */
+int sg_wprep_bwd(const float* partial, int nsplit, float* dW, int Cout, int Cin, int KK, int npt, const float* coef,
+                 float scale, int transpose, int accumulate, void* stream);
+int sg_conv_generic(const void* x, const void* E, void* y, const float* bias, float bias_mul, int act, int dtype,
+                    const SgConvGeom* g, void* stream);
+int sg_wgrad_splits(const SgConvGeom* g);
+/* partial: [nsplit][nphase*ntaps][Cin][Cout] float32 */
+int sg_wgrad_generic(const void* x, const void* dy, float* partial, int nsplit, int dtype, const SgConvGeom* g,
+                     void* stream);
+
+/* tcgen05/TMA implicit-GEMM 3x3 stride-1 convolution, bf16 operands, fp32 TMEM accumulation (csrc/sg_conv_tc.cu).
+ * x [N,H,W,Cin] bf16, Etc [9][Cout][Cin] bf16 (K-major), y [N,H,W,Cout] bf16; fused bias + LeakyReLU epilogue.
+ * The north-star kernel: blocks[i].conv1 / conv0, models/CustomLayers.py:170-171. */
+int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout);
+int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float* bias, float bias_mul, int act, int N, int H,
+                  int W, int Cin, int Cout, void* stream);
+
+/* ---- bandwidth-bound feature-map kernels ------------------------------------------------------------------------ */
+/* BlurLayer.forward, CustomLayers.py:266-276 (+ the `x + bias` of :178-179 when bias != NULL). Self-adjoint. */
+int sg_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W, int C,
+             void* stream);
+/* y = x + bias[c]*bias_mul + noise_w[c]*noise[n,p]: stand-alone NoiseLayer (CustomLayers.py:191-200) / bias add (:178). */
+int sg_bias_noise(const void* x, const float* bias, float bias_mul, const float* noise, const float* noise_w, int act,
+                  void* y, int dtype, long long P, int C, void* stream);
+/* out = a*x + b*y (y may be NULL): fade-in lerps GAN.py:202,427,586; scaling. */
+int sg_axpby(const void* x, const void* y, void* out, float a, float b, long long n, int dtype, void* stream);
+/* LeakyReLU(0.2) backward from the activation output (GAN.py:68,151,347). */
+int sg_lrelu_bwd(const void* g, const void* ref, void* gx, long long n, int dtype, void* stream);
+int sg_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, void* stream);
+/* out[j][c] = scale * sum_p wt_j(p) * x[p][c]; wt [N][J][HW] float32, optional all-ones last row.  Bias, noise-weight,
+ * from_rgb and to_rgb weight gradients.  part_ws: sg_channel_sum_blocks(P) * rows * C floats. */
+int sg_channel_sum_blocks(long long P);
+int sg_channel_sum(const void* x, int dtype, const float* wt, int J, int ones, long long P, int HW, int C,
+                   float* part_ws, float* out, float scale, int accumulate, void* stream);
+/* from_rgb: 1x1 EqualizedConv2d on the NCHW float image + LeakyReLU, GAN.py:358,377,408,423-426 */
+int sg_rgb_in(const float* img, const float* W, const float* bias, float scale, float bias_mul, int act, void* y,
+              int dtype, int N, int HW, int K, int C, void* stream);
+int sg_rgb_in_dgrad(const void* g, int dtype, const float* W, float scale, float* gimg, int N, int HW, int K, int C,
+                    void* stream);
+/* to_rgb (+ nearest x`up` of its input, + fade-in accumulate): GAN.py:157,167,173,199-202 */
+int sg_rgb_out(const void* x, int dtype, const float* W, const float* bias, float scale, float bias_mul, float alpha,
+               float beta, float* out, int N, int h, int w, int C, int K, int up, void* stream);
+int sg_rgb_out_dgrad(const float* g, const float* W, float coef, void* gx, int dtype, int N, int h, int w, int C,
+                     int K, int up, void* stream);
+/* AvgPool2d / nearest interpolate on NCHW float images: GAN.py:382, 575-586 */
+int sg_pool_nchw(const float* in, float* out, long long planes, int Ho, int Wo, int f, float scale, void* stream);
+int sg_upsample_nchw(const float* in, float* out, long long planes, int Hi, int Wi, int f, float scale, void* stream);
+int sg_plane_sum(const float* g, float* out, int N, int K, int HW, float scale, int accumulate, void* stream);
+/* style mixing + truncation: GAN.py:281-293, CustomLayers.py:319-323 */
+int sg_dlatents(const float* w1, const float* w2, const float* avg, float* out, int B, int L, int D, int mix_cutoff,
+                float psi, int trunc_cutoff, void* stream);
+int sg_dlatents_bwd(const float* g, float* gw1, float* gw2, int B, int L, int D, int mix_cutoff, float psi,
+                    int trunc_cutoff, int has_trunc, void* stream);
+
+/* ---- LayerEpilogue: NoiseLayer + LeakyReLU + InstanceNorm2d + StyleMod, CustomLayers.py:191-248 ---------------- */
+int sg_epi_act_stats(const void* y, const float* bias, float bias_mul, const float* noise, const float* noise_w,
+                     int act, void* z, double* sums, int dtype, int N, int HW, int C, void* stream);
+int sg_epi_finalize(const double* sums, const float* style, float* mr, float* ab, int N, int C, int HW, float eps,
+                    void* stream);
+int sg_affine_nc(const void* z, const float* ab, void* out, int dtype, int N, int HW, int C, void* stream);
+int sg_epi_bwd_reduce(const void* g, const void* z, const float* mr, double* sums, int dtype, int N, int HW, int C,
+                      void* stream);
+int sg_epi_bwd_finalize(const double* sums, const float* mr, const float* style, float* gstyle, float* coef, int N,
+                        int C, int HW, void* stream);
+int sg_epi_bwd_apply(const void* g, const void* z, const float* coef, int act, void* gy, int dtype, int N, int HW,
+                     int C, void* stream);
+
+/* ---- small float32 kernels -------------------------------------------------------------------------------------- */
+/* EqualizedLinear.forward, CustomLayers.py:99-103 (x rows `ldx` apart) */
+int sg_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale, float bias_mul,
+                  int act, float* y, int B, int I, int O, void* stream);
+int sg_linear_dgrad(const float* gy, const float* W, float scale, float* gx, int B, int I, int O, void* stream);
+int sg_linear_wgrad(const float* gy, const float* x, long long ldx, float scale, float bias_scale, float* gW,
+                    float* gb, int B, int I, int O, int accumulate, void* stream);
+/* PixelNormLayer, CustomLayers.py:22-23 */
+int sg_pixelnorm_fwd(const float* x, float* y, int B, int D, float eps, void* stream);
+int sg_pixelnorm_bwd(const float* g, const float* x, float* gx, int B, int D, float eps, void* stream);
+/* StddevLayer, CustomLayers.py:294-305 (NHWC float32, ws >= 2*(B/G) floats) */
+int sg_mbstd_fwd(const float* x, float* out, float* ws, int B, int HW, int C, int G, void* stream);
+int sg_mbstd_bwd(const float* gout, const float* x, float* gx, float* ws, int B, int HW, int C, int G, void* stream);
+int sg_mbstd_bwd2(const float* t, const float* gout, const float* x, float* cot_gout, float* cot_x, float* ws, int B,
+                  int HW, int C, int G, void* stream);
+/* LogisticGAN, Losses.py:213-229 */
+int sg_softplus_sum(const float* x, int n, float sign, float scale, float* out, int accumulate, void* stream);
+int sg_softplus_bwd(const float* x, int n, float sign, const float* gout, float gscale, float* gx, void* stream);
+/* R1Penalty's sum of squares, Losses.py:209 (ws: 1024 doubles) */
+int sg_sqsum(const float* x, long long n, float scale, float* out, int accumulate, double* ws, void* stream);
+int sg_scale_by_scalar(const float* x, const float* gout, float coef, float* gx, long long n, void* stream);
+
+/* ---- optimizer step: torch.optim.Adam + clip_grad_norm_ + update_average, GAN.py:529-533,651-656 ---------------- */
+int sg_chunk_elems(void);
+int sg_sqnorm_multi(const SgTensorEntry* table_dev, int T, int total_chunks, double* out_dev, void* stream);
+int sg_adam_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float lr, float beta1, float beta2,
+                  float eps, float grad_scale, const double* normsq_dev, float max_norm, float ema_beta, void* stream);
+int sg_ema_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float ema_beta, void* stream);
+/* NoiseLayer's torch.randn, CustomLayers.py:193 (Philox4x32-10 + Box-Muller) */
+int sg_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGB200_H */

@@ -1,0 +1,26 @@
+// Error reporting and library metadata for libsgb200.so.
+#include "sg_common.cuh"
+#include "../../include/sgb200.h"
+#include <string.h>
+#include <stdio.h>
+
+static thread_local char g_err[512] = {0};
+
+void sg_set_error(const char* msg) {
+  strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+
+int sg_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+SG_EXPORT const char* sg_last_error(void) { return g_err; }
+SG_EXPORT int sg_abi_version(void) { return SGB200_ABI_VERSION; }
+SG_EXPORT int sg_geom_size(void) { return (int)sizeof(SgConvGeom); }
+SG_EXPORT int sg_entry_size(void) { return (int)sizeof(SgTensorEntry); }

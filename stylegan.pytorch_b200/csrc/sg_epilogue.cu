@@ -1,0 +1,234 @@
+// Synthesis-layer epilogue (reference CustomLayers.py:219-248: noise -> LeakyReLU -> InstanceNorm -> StyleMod)
+// as two forward passes and two backward passes over NHWC activations:
+//   fwd 1  z = lrelu(y + b[c] + nw[c]*noise[n,p]);  S[n,c] += (z, z^2)            (sg_epi_act_stats)
+//   fwd 2  out = a[n,c]*z + d[n,c]   with a = rstd*(1+s0), d = s1 - mean*a        (sg_epi_finalize + sg_affine_nc)
+//   bwd 1  A[n,c] = sum_p g,  B[n,c] = sum_p g*xhat                               (sg_epi_bwd_reduce)
+//   bwd 2  g_pre = (c1*g + c2*z + c3) * lrelu'(z)                                 (sg_epi_bwd_finalize + _apply)
+// Per-(n,c) sums are accumulated in fp64 (block partials in fp32) so the one-pass variance is safe.
+#include "sg_common.cuh"
+#include "../../include/sgb200.h"
+
+namespace {
+
+constexpr int EPI_ROWS = 8;  // pixel rows per block (blockDim.y)
+
+// Two-value reduction over the pixels of one image: grid (chunks, N), block (CX, EPI_ROWS).
+// MODE 0: v = lrelu(y + b + nw*noise) -> write z, accumulate (z, z^2)
+// MODE 1: accumulate (g, g*xhat), xhat = (z-mean)*rstd
+template <class T, int MODE>
+__global__ void epi_reduce_kernel(const T* __restrict__ in0, const T* __restrict__ in1, T* __restrict__ zout,
+                                  const float* __restrict__ bias, float bias_mul, const float* __restrict__ noise,
+                                  const float* __restrict__ noise_w, const float* __restrict__ mr,
+                                  double* __restrict__ sums, int HW, int C, int pix_per_blk, int act) {
+  extern __shared__ float sm[];  // [2][EPI_ROWS][C]
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_blk;
+  int p1 = p0 + pix_per_blk;
+  if (p1 > HW) p1 = HW;
+  const size_t base = (size_t)n * HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    float b = 0.f, nw = 0.f, mean = 0.f, rstd = 0.f;
+    if (MODE == 0) {
+      b = bias ? bias[c] * bias_mul : 0.f;
+      nw = (noise && noise_w) ? noise_w[c] : 0.f;
+    } else {
+      mean = mr[((size_t)n * C + c) * 2 + 0];
+      rstd = mr[((size_t)n * C + c) * 2 + 1];
+    }
+    for (int p = p0 + threadIdx.y; p < p1; p += EPI_ROWS) {
+      size_t idx = (base + p) * C + c;
+      if (MODE == 0) {
+        float v = sg_to_f(in0[idx]) + b;
+        if (noise) v = fmaf(nw, noise[base + p], v);
+        if (act) v = sg_lrelu(v);
+        T zt = sg_from_f<T>(v);
+        zout[idx] = zt;
+        float zr = sg_to_f(zt);
+        s0 += zr;
+        s1 = fmaf(zr, zr, s1);
+      } else {
+        float g = sg_to_f(in0[idx]);
+        float xh = (sg_to_f(in1[idx]) - mean) * rstd;
+        s0 += g;
+        s1 = fmaf(g, xh, s1);
+      }
+    }
+    sm[(0 * EPI_ROWS + threadIdx.y) * C + c] = s0;
+    sm[(1 * EPI_ROWS + threadIdx.y) * C + c] = s1;
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < 2 * C; i += nthr) {
+    int j = i / C, c = i % C;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < EPI_ROWS; ++r) s += sm[(j * EPI_ROWS + r) * C + c];
+    atomicAdd(&sums[((size_t)n * C + c) * 2 + j], (double)s);
+  }
+}
+
+// per-(n,c): mean/rstd and the fused affine (a, d).  style = [N, 2C] (s0 | s1); style may be null (plain IN).
+__global__ void epi_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ style,
+                                    float* __restrict__ mr, float* __restrict__ ab, int N, int C, int HW, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  int n = i / C, c = i % C;
+  double m = sums[(size_t)i * 2] / HW;
+  double var = sums[(size_t)i * 2 + 1] / HW - m * m;
+  if (var < 0.0) var = 0.0;
+  float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  float mean = (float)m;
+  mr[(size_t)i * 2] = mean;
+  mr[(size_t)i * 2 + 1] = rstd;
+  float s0 = style ? style[(size_t)n * 2 * C + c] : 0.f;
+  float s1 = style ? style[(size_t)n * 2 * C + C + c] : 0.f;
+  float a = rstd * (1.f + s0);
+  ab[(size_t)i * 2] = a;
+  ab[(size_t)i * 2 + 1] = s1 - mean * a;
+}
+
+// out[n,p,c] = ab[n,c,0]*z + ab[n,c,1]
+template <class T>
+__global__ void affine_nc_kernel(const T* __restrict__ z, const float* __restrict__ ab, T* __restrict__ out, int N,
+                                 int HW, int C) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const long long total = (long long)N * HW * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int n = (int)(p / HW);
+    V v, o;
+    v.load(z + (size_t)p * C + cv * V::N);
+    const float* q = ab + ((size_t)n * C + cv * V::N) * 2;
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) o.set(k, fmaf(q[2 * k], v.get(k), q[2 * k + 1]));
+    o.store(out + (size_t)p * C + cv * V::N);
+  }
+}
+template <class T>
+__global__ void affine_nc_scalar_kernel(const T* __restrict__ z, const float* __restrict__ ab, T* __restrict__ out,
+                                        int N, int HW, int C) {
+  const long long total = (long long)N * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int n = (int)(i / ((long long)HW * C));
+    const float* q = ab + ((size_t)n * C + c) * 2;
+    out[i] = sg_from_f<T>(fmaf(q[0], sg_to_f(z[i]), q[1]));
+  }
+}
+
+// per-(n,c): style gradients and the coefficients of  g_z = c1*g + c2*z + c3
+__global__ void epi_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ mr,
+                                        const float* __restrict__ style, float* __restrict__ gstyle,
+                                        float* __restrict__ coef, int N, int C, int HW) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  int n = i / C, c = i % C;
+  float A = (float)sums[(size_t)i * 2], B = (float)sums[(size_t)i * 2 + 1];
+  float mean = mr[(size_t)i * 2], rstd = mr[(size_t)i * 2 + 1];
+  float s0 = style ? style[(size_t)n * 2 * C + c] : 0.f;
+  if (gstyle) {
+    gstyle[(size_t)n * 2 * C + c] = B;       // d/ds0 = sum g * xhat
+    gstyle[(size_t)n * 2 * C + C + c] = A;   // d/ds1 = sum g
+  }
+  float inv = 1.f / (float)HW;
+  float c1 = rstd * (1.f + s0);
+  float c2 = -c1 * rstd * B * inv;
+  float c3 = c1 * (mean * rstd * B * inv - A * inv);
+  coef[(size_t)i * 3] = c1;
+  coef[(size_t)i * 3 + 1] = c2;
+  coef[(size_t)i * 3 + 2] = c3;
+}
+
+template <class T>
+__global__ void epi_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ z, const float* __restrict__ coef,
+                                     T* __restrict__ gy, int N, int HW, int C, int act) {
+  const long long total = (long long)N * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int n = (int)(i / ((long long)HW * C));
+    const float* q = coef + ((size_t)n * C + c) * 3;
+    float zv = sg_to_f(z[i]);
+    float gz = fmaf(q[0], sg_to_f(g[i]), fmaf(q[1], zv, q[2]));
+    gy[i] = sg_from_f<T>((!act || zv > 0.f) ? gz : SG_LRELU_SLOPE * gz);
+  }
+}
+
+template <class T, int MODE>
+int launch_reduce(const void* in0, const void* in1, void* zout, const float* bias, float bias_mul, const float* noise,
+                  const float* noise_w, const float* mr, double* sums, int N, int HW, int C, int act, cudaStream_t st) {
+  int bx = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+  dim3 block(bx, EPI_ROWS);
+  // aim for >= ~4 waves of CTAs; each CTA at least 64 pixels
+  int chunks = (148 * 4 + N - 1) / N;
+  int maxchunks = (HW + 63) / 64;
+  if (chunks > maxchunks) chunks = maxchunks;
+  if (chunks < 1) chunks = 1;
+  int pix_per_blk = (HW + chunks - 1) / chunks;
+  chunks = (HW + pix_per_blk - 1) / pix_per_blk;
+  size_t smem = (size_t)2 * EPI_ROWS * C * sizeof(float);
+  if (smem > 48 * 1024) { sg_set_error("epilogue: C too large"); return 1000; }
+  dim3 grid(chunks, N);
+  epi_reduce_kernel<T, MODE><<<grid, block, smem, st>>>((const T*)in0, (const T*)in1, (T*)zout, bias, bias_mul, noise,
+                                                        noise_w, mr, sums, HW, C, pix_per_blk, act);
+  return sg_check_launch("epi_reduce");
+}
+
+}  // namespace
+
+// sums must be zeroed by the caller (N*C*2 doubles).
+SG_EXPORT int sg_epi_act_stats(const void* y, const float* bias, float bias_mul, const float* noise,
+                               const float* noise_w, int act, void* z, double* sums, int dtype, int N, int HW,
+                               int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, { return launch_reduce<T, 0>(y, nullptr, z, bias, bias_mul, noise, noise_w, nullptr, sums, N, HW, C, act, st); });
+  return 0;
+}
+
+SG_EXPORT int sg_epi_finalize(const double* sums, const float* style, float* mr, float* ab, int N, int C, int HW,
+                              float eps, void* stream) {
+  epi_finalize_kernel<<<sg_cdiv((long long)N * C, 128), 128, 0, (cudaStream_t)stream>>>(sums, style, mr, ab, N, C, HW, eps);
+  return sg_check_launch("sg_epi_finalize");
+}
+
+SG_EXPORT int sg_affine_nc(const void* z, const float* ab, void* out, int dtype, int N, int HW, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    if (C % SgVec<T>::N == 0) {
+      long long total = (long long)N * HW * (C / SgVec<T>::N);
+      affine_nc_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)z, ab, (T*)out, N, HW, C);
+    } else {
+      long long total = (long long)N * HW * C;
+      affine_nc_scalar_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)z, ab, (T*)out, N, HW, C);
+    }
+  });
+  return sg_check_launch("sg_affine_nc");
+}
+
+SG_EXPORT int sg_epi_bwd_reduce(const void* g, const void* z, const float* mr, double* sums, int dtype, int N, int HW,
+                                int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, { return launch_reduce<T, 1>(g, z, nullptr, nullptr, 0.f, nullptr, nullptr, mr, sums, N, HW, C, 0, st); });
+  return 0;
+}
+
+SG_EXPORT int sg_epi_bwd_finalize(const double* sums, const float* mr, const float* style, float* gstyle, float* coef,
+                                  int N, int C, int HW, void* stream) {
+  epi_bwd_finalize_kernel<<<sg_cdiv((long long)N * C, 128), 128, 0, (cudaStream_t)stream>>>(sums, mr, style, gstyle, coef, N, C, HW);
+  return sg_check_launch("sg_epi_bwd_finalize");
+}
+
+SG_EXPORT int sg_epi_bwd_apply(const void* g, const void* z, const float* coef, int act, void* gy, int dtype, int N,
+                               int HW, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  long long total = (long long)N * HW * C;
+  SG_DISPATCH(dtype, {
+    epi_bwd_apply_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)g, (const T*)z, coef, (T*)gy, N, HW, C, act);
+  });
+  return sg_check_launch("sg_epi_bwd_apply");
+}

@@ -1,0 +1,155 @@
+// Multi-tensor optimizer step (Adam + global-norm clip + 1/world gradient scale + generator EMA), gradient
+// square-norm, and the Philox normal generator used by NoiseLayer.
+// reference: GAN.py:529-533 (Adam), GAN.py:651 (clip_grad_norm_), models/__init__.py:13-40 (update_average),
+//            CustomLayers.py:193 (torch.randn noise).
+#include "sg_common.cuh"
+#include "../../include/sgb200.h"
+
+namespace {
+
+constexpr int CHUNK = 2048;  // elements per block
+
+__device__ __forceinline__ int find_entry(const SgTensorEntry* __restrict__ tab, int T, int chunk) {
+  int lo = 0, hi = T - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].chunk0 <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void sqnorm_multi_kernel(const SgTensorEntry* __restrict__ tab, int T, double* __restrict__ out) {
+  __shared__ float sm[32];
+  const int e = find_entry(tab, T, blockIdx.x);
+  const SgTensorEntry en = tab[e];
+  const float* g = reinterpret_cast<const float*>(en.g);
+  long long i0 = (long long)(blockIdx.x - en.chunk0) * CHUNK;
+  long long i1 = i0 + CHUNK < en.n ? i0 + CHUNK : en.n;
+  float s = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) { float v = g[i]; s = fmaf(v, v, s); }
+  s = sg_block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(out, (double)s);
+}
+
+__global__ void adam_multi_kernel(const SgTensorEntry* __restrict__ tab, int T, float lr, float beta1, float beta2,
+                                  float eps, float grad_scale, const double* __restrict__ normsq, float max_norm,
+                                  float ema_beta) {
+  const int e = find_entry(tab, T, blockIdx.x);
+  const SgTensorEntry en = tab[e];
+  float* p = reinterpret_cast<float*>(en.p);
+  const float* g = reinterpret_cast<const float*>(en.g);
+  float* m = reinterpret_cast<float*>(en.m);
+  float* v = reinterpret_cast<float*>(en.v);
+  float* ema = reinterpret_cast<float*>(en.ema);
+  const float t = *reinterpret_cast<const float*>(en.step) + 1.f;
+  const float bc1 = 1.f - powf(beta1, t);
+  const float bc2 = 1.f - powf(beta2, t);
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  float gs = grad_scale;
+  if (normsq != nullptr) {
+    // clip_grad_norm_: coef = min(1, max_norm / (||g|| + 1e-6)) on the already-scaled gradient
+    float total = (float)sqrt(*normsq) * grad_scale;
+    float coef = max_norm / (total + 1e-6f);
+    if (coef < 1.f) gs *= coef;
+  }
+  long long i0 = (long long)(blockIdx.x - en.chunk0) * CHUNK;
+  long long i1 = i0 + CHUNK < en.n ? i0 + CHUNK : en.n;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    float gv = g[i] * gs;
+    float mv = beta1 * m[i] + (1.f - beta1) * gv;
+    float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    float pv = p[i] - step_size * (mv / denom);
+    p[i] = pv;
+    if (ema) ema[i] = ema_beta * ema[i] + (1.f - ema_beta) * pv;
+  }
+}
+
+__global__ void bump_steps_kernel(const SgTensorEntry* __restrict__ tab, int T) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) *reinterpret_cast<float*>(tab[i].step) += 1.f;
+}
+
+// EMA only (parameters with no gradient this step still get averaged: models/__init__.py:33-36 loops over all)
+__global__ void ema_multi_kernel(const SgTensorEntry* __restrict__ tab, int T, float ema_beta) {
+  const int e = find_entry(tab, T, blockIdx.x);
+  const SgTensorEntry en = tab[e];
+  const float* p = reinterpret_cast<const float*>(en.p);
+  float* ema = reinterpret_cast<float*>(en.ema);
+  long long i0 = (long long)(blockIdx.x - en.chunk0) * CHUNK;
+  long long i1 = i0 + CHUNK < en.n ? i0 + CHUNK : en.n;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) ema[i] = ema_beta * ema[i] + (1.f - ema_beta) * p[i];
+}
+
+// ---- Philox4x32-10 + Box-Muller ----------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset) {
+  const long long nq = (n + 3) / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    unsigned long long ctr = offset + (unsigned long long)q;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5347u, 0xB200u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    float u0 = ((float)c[0] + 0.5f) * (1.f / 4294967296.f);
+    float u1 = ((float)c[1] + 0.5f) * (1.f / 4294967296.f);
+    float u2 = ((float)c[2] + 0.5f) * (1.f / 4294967296.f);
+    float u3 = ((float)c[3] + 0.5f) * (1.f / 4294967296.f);
+    if (u0 < 1e-37f) u0 = 1e-37f;
+    if (u2 < 1e-37f) u2 = 1e-37f;
+    float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u1, &s0, &c0);
+    sincospif(2.f * u3, &s1, &c1);
+    float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (q * 4 + k < n) out[q * 4 + k] = z[k];
+  }
+}
+
+}  // namespace
+
+SG_EXPORT int sg_chunk_elems(void) { return CHUNK; }
+
+SG_EXPORT int sg_sqnorm_multi(const SgTensorEntry* table_dev, int T, int total_chunks, double* out_dev, void* stream) {
+  if (T <= 0 || total_chunks <= 0) return 0;
+  sqnorm_multi_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, T, out_dev);
+  return sg_check_launch("sg_sqnorm_multi");
+}
+
+SG_EXPORT int sg_adam_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float lr, float beta1, float beta2,
+                            float eps, float grad_scale, const double* normsq_dev, float max_norm, float ema_beta,
+                            void* stream) {
+  if (T <= 0 || total_chunks <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_multi_kernel<<<total_chunks, 256, 0, st>>>(table_dev, T, lr, beta1, beta2, eps, grad_scale, normsq_dev, max_norm, ema_beta);
+  int rc = sg_check_launch("sg_adam_multi");
+  if (rc) return rc;
+  bump_steps_kernel<<<sg_cdiv(T, 128), 128, 0, st>>>(table_dev, T);
+  return sg_check_launch("sg_adam_multi/steps");
+}
+
+SG_EXPORT int sg_ema_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float ema_beta, void* stream) {
+  if (T <= 0 || total_chunks <= 0) return 0;
+  ema_multi_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, T, ema_beta);
+  return sg_check_launch("sg_ema_multi");
+}
+
+SG_EXPORT int sg_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream) {
+  randn_kernel<<<sg_grid_1d((n + 3) / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+  return sg_check_launch("sg_randn");
+}

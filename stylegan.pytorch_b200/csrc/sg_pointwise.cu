@@ -1,0 +1,560 @@
+// Bandwidth-bound NHWC kernels: blur, axpby/lerp, LeakyReLU backward, casts, per-channel reductions, from/to-RGB
+// pointwise convolutions (NCHW fp32 image side <-> NHWC feature side), image pooling, dlatent assembly.
+#include "sg_common.cuh"
+#include "../../include/sgb200.h"
+
+namespace {
+
+__device__ __forceinline__ float pick4(const float (&a)[4], int k) {
+  return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3]));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// depthwise [1,2,1]x[1,2,1]/16 blur, zero pad 1, optional +bias[c]*bias_mul.   reference CustomLayers.py:251-276
+// self-adjoint, so the same kernel is its own backward (without bias).
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void blur3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ bias,
+                             float bias_mul, int N, int H, int W, int C) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const long long total = (long long)N * H * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int w = (int)(p % W);
+    long long r = p / W;
+    int h = (int)(r % H);
+    int n = (int)(r / H);
+    float acc[V::N];
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      int hh = h + dy;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        int ww = w + dx;
+        if (ww < 0 || ww >= W) continue;
+        float kw = (dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * (1.f / 16.f);
+        V v;
+        v.load(x + (((size_t)n * H + hh) * W + ww) * C + cv * V::N);
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) acc[k] = fmaf(kw, v.get(k), acc[k]);
+      }
+    }
+    V o;
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) {
+      float b = bias ? bias[cv * V::N + k] * bias_mul : 0.f;
+      o.set(k, acc[k] + b);
+    }
+    o.store(y + (size_t)p * C + cv * V::N);
+  }
+}
+
+// scalar fallback for C not a multiple of the vector width
+template <class T>
+__global__ void blur3_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ bias,
+                                    float bias_mul, int N, int H, int W, int C) {
+  const long long total = (long long)N * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int w = (int)(p % W);
+    long long r = p / W;
+    int h = (int)(r % H);
+    int n = (int)(r / H);
+    float acc = 0.f;
+    for (int dy = -1; dy <= 1; ++dy) {
+      int hh = h + dy;
+      if (hh < 0 || hh >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        int ww = w + dx;
+        if (ww < 0 || ww >= W) continue;
+        float kw = (dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * (1.f / 16.f);
+        acc = fmaf(kw, sg_to_f(x[(((size_t)n * H + hh) * W + ww) * C + c]), acc);
+      }
+    }
+    y[i] = sg_from_f<T>(acc + (bias ? bias[c] * bias_mul : 0.f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out = a*x + b*y   (y may be null).  Used for fade-in lerps (GAN.py:202,427,586), scaling, EMA-style updates.
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, float a, float b,
+                             long long n) {
+  using V = SgVec<T>;
+  const long long nv = n / V::N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    V vx, vy, vo;
+    vx.load(x + i * V::N);
+    if (y) vy.load(y + i * V::N); else vy.zero();
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) vo.set(k, a * vx.get(k) + b * vy.get(k));
+    vo.store(out + i * V::N);
+  }
+  // tail
+  for (long long i = nv * V::N + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = sg_from_f<T>(a * sg_to_f(x[i]) + (y ? b * sg_to_f(y[i]) : 0.f));
+}
+
+// gx = g * (ref > 0 ? 1 : slope): backward of LeakyReLU given its OUTPUT (or input; same sign).
+template <class T>
+__global__ void lrelu_bwd_kernel(const T* __restrict__ g, const T* __restrict__ ref, T* __restrict__ gx,
+                                 long long n) {
+  using V = SgVec<T>;
+  const long long nv = n / V::N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    V vg, vr, vo;
+    vg.load(g + i * V::N);
+    vr.load(ref + i * V::N);
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) vo.set(k, vr.get(k) > 0.f ? vg.get(k) : SG_LRELU_SLOPE * vg.get(k));
+    vo.store(gx + i * V::N);
+  }
+  for (long long i = nv * V::N + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    gx[i] = sg_from_f<T>(sg_to_f(ref[i]) > 0.f ? sg_to_f(g[i]) : SG_LRELU_SLOPE * sg_to_f(g[i]));
+}
+
+template <class TI, class TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = sg_from_f<TO>(sg_to_f(x[i]));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weighted per-channel reduction over pixels:  part[blk][j][c] = sum_{p in blk} wt_j(p) * x[p][c]
+//   rows j = 0..J-1 use wt[(n*J + j)*HW + hw]  (p = n*HW + hw);  if `ones` an extra last row uses weight 1.
+// Stage 2 sums the partials deterministically.  Used for bias / noise-weight / from_rgb / to_rgb gradients.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS = 4;  // max J + ones
+template <class T>
+__global__ void channel_sum_kernel(const T* __restrict__ x, const float* __restrict__ wt, int J, int ones,
+                                   long long P, int HW, int C, float* __restrict__ part, int pix_per_blk) {
+  extern __shared__ float sm[];  // [rows][R][C] reduced over R at the end
+  const int R = blockDim.y;
+  const int rows = J + (ones ? 1 : 0);
+  const long long p0 = (long long)blockIdx.x * pix_per_blk;
+  long long p1 = p0 + pix_per_blk;
+  if (p1 > P) p1 = P;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[CS_ROWS];
+#pragma unroll
+    for (int j = 0; j < CS_ROWS; ++j) acc[j] = 0.f;
+    for (long long p = p0 + threadIdx.y; p < p1; p += R) {
+      float v = sg_to_f(x[(size_t)p * C + c]);
+      long long n = p / HW;
+      int hw = (int)(p - n * HW);
+#pragma unroll
+      for (int j = 0; j < CS_ROWS; ++j) {
+        if (j < J) acc[j] = fmaf(wt[((size_t)n * J + j) * HW + hw], v, acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < CS_ROWS; ++j)
+        if (ones && j == J) acc[j] += v;
+    }
+    for (int j = 0; j < rows; ++j) sm[((size_t)j * R + threadIdx.y) * C + c] = pick4(acc, j);
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < rows * C; i += nthr) {
+    int j = i / C, c = i % C;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += sm[((size_t)j * R + r) * C + c];
+    part[((size_t)blockIdx.x * rows + j) * C + c] = s;
+  }
+}
+
+__global__ void partial_reduce_kernel(const float* __restrict__ part, int nblk, int M, float* __restrict__ out,
+                                      float scale, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * M + i];
+  out[i] = (accumulate ? out[i] : 0.f) + s * scale;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// from_rgb: img fp32 NCHW [N,K,H,W] -> y NHWC T [N,H,W,C]:  y = act(scale * sum_k W[c][k] img[k] + b[c]*bmul)
+// reference GAN.py:358,377 (1x1 EqualizedConv2d) + LeakyReLU.  K <= 4.
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void rgb_in_kernel(const float* __restrict__ img, const float* __restrict__ Wt, const float* __restrict__ bias,
+                              float scale, float bias_mul, int act, T* __restrict__ y, int N, int HW, int K, int C) {
+  const long long total = (long long)N * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    long long n = p / HW;
+    int hw = (int)(p - n * HW);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s = fmaf(Wt[c * K + k], img[((size_t)n * K + k) * HW + hw], s);
+    s = s * scale + (bias ? bias[c] * bias_mul : 0.f);
+    if (act) s = sg_lrelu(s);
+    y[i] = sg_from_f<T>(s);
+  }
+}
+
+// adjoint wrt the image: gimg[n,k,hw] = scale * sum_c g[n,hw,c] * W[c][k]     (one sub-warp group per pixel)
+template <class T>
+__global__ void rgb_in_dgrad_kernel(const T* __restrict__ g, const float* __restrict__ Wt, float scale,
+                                    float* __restrict__ gimg, int N, int HW, int K, int C) {
+  const long long P = (long long)N * HW;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < P; p += nwarps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < C; c += 32) {
+      float v = sg_to_f(g[(size_t)p * C + c]);
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(v, Wt[c * K + k], acc[k]);
+    }
+    for (int k = 0; k < K; ++k) acc[k] = sg_warp_sum(acc[k]);
+    if (lane < K) {
+      long long n = p / HW;
+      int hw = (int)(p - n * HW);
+      gimg[((size_t)n * K + lane) * HW + hw] = pick4(acc, lane) * scale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// to_rgb: x NHWC T [N,h,w,C] -> out fp32 NCHW [N,K,h*up,w*up]:
+//   out = beta*out + alpha*(scale * sum_c W[k][c] x[c] + b[k]*bmul), nearest-upsampled by `up`.
+// reference GAN.py:157,167 (1x1 conv, gain 1), GAN.py:199-202 (temporaryUpsampler + fade-in lerp).
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void rgb_out_kernel(const T* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
+                               float scale, float bias_mul, float alpha, float beta, float* __restrict__ out, int N,
+                               int h, int w, int C, int K, int up) {
+  const long long P = (long long)N * h * w;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int H = h * up, Wd = w * up;
+  for (long long p = warp; p < P; p += nwarps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < C; c += 32) {
+      float v = sg_to_f(x[(size_t)p * C + c]);
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(v, Wt[k * C + c], acc[k]);
+    }
+    for (int k = 0; k < K; ++k) acc[k] = sg_warp_sum(acc[k]);
+    int xw = (int)(p % w);
+    long long r = p / w;
+    int yh = (int)(r % h);
+    int n = (int)(r / h);
+    // lanes spread over (k, a, b)
+    for (int j = lane; j < K * up * up; j += 32) {
+      int k = j / (up * up), ab = j % (up * up), a = ab / up, b = ab % up;
+      float val = alpha * (pick4(acc, k) * scale + (bias ? bias[k] * bias_mul : 0.f));
+      size_t o = (((size_t)n * K + k) * H + (yh * up + a)) * Wd + (xw * up + b);
+      out[o] = (beta != 0.f ? beta * out[o] : 0.f) + val;
+    }
+  }
+}
+
+// adjoint wrt x: gx[n,y,x,c] = alpha*scale * sum_k W[k][c] * sum_{a,b<up} g[n,k,y*up+a,x*up+b]
+template <class T>
+__global__ void rgb_out_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ Wt, float coef,
+                                     T* __restrict__ gx, int N, int h, int w, int C, int K, int up) {
+  const long long total = (long long)N * h * w * C;
+  const int H = h * up, Wd = w * up;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int xw = (int)(p % w);
+    long long r = p / w;
+    int yh = (int)(r % h);
+    int n = (int)(r / h);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float gs = 0.f;
+      for (int a = 0; a < up; ++a)
+        for (int b = 0; b < up; ++b) gs += g[(((size_t)n * K + k) * H + (yh * up + a)) * Wd + (xw * up + b)];
+      s = fmaf(Wt[k * C + c], gs, s);
+    }
+    gx[i] = sg_from_f<T>(s * coef);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 NCHW image helpers: box pooling / nearest up-sampling (adjoint pair).   reference GAN.py:382,575-586
+// ---------------------------------------------------------------------------------------------------------
+__global__ void pool_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int Ho,
+                                 int Wo, int f, float scale) {
+  const long long total = planes * Ho * Wo;
+  const int Wi = Wo * f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % Wo);
+    long long r = i / Wo;
+    int y = (int)(r % Ho);
+    long long pl = r / Ho;
+    const float* src = in + (pl * Ho * f + (long long)y * f) * Wi + (long long)x * f;
+    float s = 0.f;
+    for (int a = 0; a < f; ++a)
+      for (int b = 0; b < f; ++b) s += src[(long long)a * Wi + b];
+    out[i] = s * scale;
+  }
+}
+
+__global__ void upsample_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int Hi,
+                                     int Wi, int f, float scale) {
+  const int Ho = Hi * f, Wo = Wi * f;
+  const long long total = planes * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % Wo);
+    long long r = i / Wo;
+    int y = (int)(r % Ho);
+    long long pl = r / Ho;
+    out[i] = in[(pl * Hi + y / f) * Wi + x / f] * scale;
+  }
+}
+
+// out[k] = scale * sum_{n,hw} g[n,k,hw]  (to_rgb bias gradient); one block per k
+__global__ void plane_sum_kernel(const float* __restrict__ g, float* __restrict__ out, int N, int K, int HW,
+                                 float scale, int accumulate) {
+  __shared__ float sm[32];
+  int k = blockIdx.x;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n)
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += g[((size_t)n * K + k) * HW + i];
+  s = sg_block_sum(s, sm);
+  if (threadIdx.x == 0) out[k] = (accumulate ? out[k] : 0.f) + s * scale;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dlatent assembly: style mixing + truncation.   reference GAN.py:281-293, CustomLayers.py:319-323
+//   src = l < mix_cutoff ? w1[b] : w2[b];   out[b,l] = l < trunc_cutoff ? avg + psi*(src-avg) : src
+// ---------------------------------------------------------------------------------------------------------
+__global__ void dlatents_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
+                                const float* __restrict__ avg, float* __restrict__ out, int B, int L, int D,
+                                int mix_cutoff, float psi, int trunc_cutoff) {
+  const long long total = (long long)B * L * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int d = (int)(i % D);
+    long long r = i / D;
+    int l = (int)(r % L);
+    int b = (int)(r / L);
+    float s = (w2 == nullptr || l < mix_cutoff) ? w1[(size_t)b * D + d] : w2[(size_t)b * D + d];
+    if (avg != nullptr && l < trunc_cutoff) { float a = avg[d]; s = a + psi * (s - a); }
+    out[i] = s;
+  }
+}
+
+__global__ void dlatents_bwd_kernel(const float* __restrict__ g, float* __restrict__ gw1, float* __restrict__ gw2,
+                                    int B, int L, int D, int mix_cutoff, float psi, int trunc_cutoff, int has_trunc) {
+  const long long total = (long long)B * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int d = (int)(i % D);
+    int b = (int)(i / D);
+    float s1 = 0.f, s2 = 0.f;
+    for (int l = 0; l < L; ++l) {
+      float v = g[((size_t)b * L + l) * D + d] * ((has_trunc && l < trunc_cutoff) ? psi : 1.f);
+      if (gw2 == nullptr || l < mix_cutoff) s1 += v; else s2 += v;
+    }
+    gw1[i] = s1;
+    if (gw2) gw2[i] = s2;
+  }
+}
+
+// y = x + bias[c]*bias_mul + noise_w[c]*noise[n,p]   (stand-alone NoiseLayer / bias add; CustomLayers.py:191-200,178)
+template <class T>
+__global__ void bias_noise_kernel(const T* __restrict__ x, const float* __restrict__ bias, float bias_mul,
+                                  const float* __restrict__ noise, const float* __restrict__ noise_w,
+                                  T* __restrict__ y, long long P, int C, int act) {
+  const long long total = P * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    float v = sg_to_f(x[i]);
+    if (bias) v = fmaf(bias[c], bias_mul, v);
+    if (noise) v = fmaf(noise_w[c], noise[p], v);
+    if (act) v = sg_lrelu(v);
+    y[i] = sg_from_f<T>(v);
+  }
+}
+
+}  // namespace
+
+SG_EXPORT int sg_bias_noise(const void* x, const float* bias, float bias_mul, const float* noise,
+                            const float* noise_w, int act, void* y, int dtype, long long P, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    bias_noise_kernel<T><<<sg_grid_1d(P * C, 256, 148 * 32), 256, 0, st>>>((const T*)x, bias, bias_mul, noise, noise_w, (T*)y, P, C, act);
+  });
+  return sg_check_launch("sg_bias_noise");
+}
+
+SG_EXPORT int sg_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W,
+                       int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    if (C % SgVec<T>::N == 0) {
+      long long total = (long long)N * H * W * (C / SgVec<T>::N);
+      blur3_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)x, (T*)y, bias, bias_mul, N, H, W, C);
+    } else {
+      long long total = (long long)N * H * W * C;
+      blur3_scalar_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)x, (T*)y, bias, bias_mul, N, H, W, C);
+    }
+  });
+  return sg_check_launch("sg_blur3");
+}
+
+SG_EXPORT int sg_axpby(const void* x, const void* y, void* out, float a, float b, long long n, int dtype,
+                       void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    axpby_kernel<T><<<sg_grid_1d(n / SgVec<T>::N + 1, 256, 148 * 32), 256, 0, st>>>((const T*)x, (const T*)y, (T*)out, a, b, n);
+  });
+  return sg_check_launch("sg_axpby");
+}
+
+SG_EXPORT int sg_lrelu_bwd(const void* g, const void* ref, void* gx, long long n, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    lrelu_bwd_kernel<T><<<sg_grid_1d(n / SgVec<T>::N + 1, 256, 148 * 32), 256, 0, st>>>((const T*)g, (const T*)ref, (T*)gx, n);
+  });
+  return sg_check_launch("sg_lrelu_bwd");
+}
+
+SG_EXPORT int sg_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = sg_grid_1d(n, 256, 148 * 32);
+  if (dtype_in == SG_F32 && dtype_out == SG_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
+  else if (dtype_in == SG_BF16 && dtype_out == SG_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
+  else if (dtype_in == SG_F32 && dtype_out == SG_F32)
+    cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
+  else if (dtype_in == SG_BF16 && dtype_out == SG_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+  else { sg_set_error("sg_cast: bad dtype"); return 1001; }
+  return sg_check_launch("sg_cast");
+}
+
+SG_EXPORT int sg_channel_sum_blocks(long long P) {
+  long long b = (P + 255) / 256;
+  if (b > 148 * 4) b = 148 * 4;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+SG_EXPORT int sg_channel_sum(const void* x, int dtype, const float* wt, int J, int ones, long long P, int HW, int C,
+                             float* part_ws, float* out, float scale, int accumulate, void* stream) {
+  int rows = J + (ones ? 1 : 0);
+  SG_REQUIRE(rows >= 1 && rows <= CS_ROWS && J >= 0, "sg_channel_sum: rows must be 1..4");
+  SG_REQUIRE(J == 0 || wt != nullptr, "sg_channel_sum: weights missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  int nblk = sg_channel_sum_blocks(P);
+  int pix_per_blk = (int)((P + nblk - 1) / nblk);
+  int bx = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+  int R = 256 / bx;
+  size_t smem = (size_t)rows * R * C * sizeof(float);
+  while (smem > 48 * 1024 && R > 1) { R >>= 1; smem = (size_t)rows * R * C * sizeof(float); }
+  SG_REQUIRE(smem <= 48 * 1024, "sg_channel_sum: C too large");
+  dim3 block(bx, R);
+  SG_DISPATCH(dtype, {
+    channel_sum_kernel<T><<<nblk, block, smem, st>>>((const T*)x, wt, J, ones, P, HW, C, part_ws, pix_per_blk);
+  });
+  int rc = sg_check_launch("sg_channel_sum");
+  if (rc) return rc;
+  int M = rows * C;
+  partial_reduce_kernel<<<sg_cdiv(M, 128), 128, 0, st>>>(part_ws, nblk, M, out, scale, accumulate);
+  return sg_check_launch("sg_channel_sum/reduce");
+}
+
+SG_EXPORT int sg_rgb_in(const float* img, const float* W, const float* bias, float scale, float bias_mul, int act,
+                        void* y, int dtype, int N, int HW, int K, int C, void* stream) {
+  SG_REQUIRE(K >= 1 && K <= 4, "sg_rgb_in: K must be 1..4");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long total = (long long)N * HW * C;
+  SG_DISPATCH(dtype, {
+    rgb_in_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);
+  });
+  return sg_check_launch("sg_rgb_in");
+}
+
+SG_EXPORT int sg_rgb_in_dgrad(const void* g, int dtype, const float* W, float scale, float* gimg, int N, int HW,
+                              int K, int C, void* stream) {
+  SG_REQUIRE(K >= 1 && K <= 4, "sg_rgb_in_dgrad: K must be 1..4");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long P = (long long)N * HW;
+  SG_DISPATCH(dtype, {
+    rgb_in_dgrad_kernel<T><<<sg_grid_1d(P * 32, 256, 148 * 16), 256, 0, st>>>((const T*)g, W, scale, gimg, N, HW, K, C);
+  });
+  return sg_check_launch("sg_rgb_in_dgrad");
+}
+
+SG_EXPORT int sg_rgb_out(const void* x, int dtype, const float* W, const float* bias, float scale, float bias_mul,
+                         float alpha, float beta, float* out, int N, int h, int w, int C, int K, int up, void* stream) {
+  SG_REQUIRE(K >= 1 && K <= 4 && up >= 1 && up <= 2, "sg_rgb_out: K must be 1..4, up 1..2");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long P = (long long)N * h * w;
+  SG_DISPATCH(dtype, {
+    rgb_out_kernel<T><<<sg_grid_1d(P * 32, 256, 148 * 16), 256, 0, st>>>((const T*)x, W, bias, scale, bias_mul, alpha, beta, out, N, h, w, C, K, up);
+  });
+  return sg_check_launch("sg_rgb_out");
+}
+
+SG_EXPORT int sg_rgb_out_dgrad(const float* g, const float* W, float coef, void* gx, int dtype, int N, int h, int w,
+                               int C, int K, int up, void* stream) {
+  SG_REQUIRE(K >= 1 && K <= 4 && up >= 1 && up <= 2, "sg_rgb_out_dgrad: K must be 1..4, up 1..2");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long total = (long long)N * h * w * C;
+  SG_DISPATCH(dtype, {
+    rgb_out_dgrad_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(g, W, coef, (T*)gx, N, h, w, C, K, up);
+  });
+  return sg_check_launch("sg_rgb_out_dgrad");
+}
+
+SG_EXPORT int sg_pool_nchw(const float* in, float* out, long long planes, int Ho, int Wo, int f, float scale,
+                           void* stream) {
+  long long total = planes * Ho * Wo;
+  pool_nchw_kernel<<<sg_grid_1d(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Ho, Wo, f, scale);
+  return sg_check_launch("sg_pool_nchw");
+}
+
+SG_EXPORT int sg_upsample_nchw(const float* in, float* out, long long planes, int Hi, int Wi, int f, float scale,
+                               void* stream) {
+  long long total = planes * Hi * f * Wi * f;
+  upsample_nchw_kernel<<<sg_grid_1d(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hi, Wi, f, scale);
+  return sg_check_launch("sg_upsample_nchw");
+}
+
+SG_EXPORT int sg_plane_sum(const float* g, float* out, int N, int K, int HW, float scale, int accumulate,
+                           void* stream) {
+  plane_sum_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(g, out, N, K, HW, scale, accumulate);
+  return sg_check_launch("sg_plane_sum");
+}
+
+SG_EXPORT int sg_dlatents(const float* w1, const float* w2, const float* avg, float* out, int B, int L, int D,
+                          int mix_cutoff, float psi, int trunc_cutoff, void* stream) {
+  long long total = (long long)B * L * D;
+  dlatents_kernel<<<sg_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(w1, w2, avg, out, B, L, D, mix_cutoff, psi, trunc_cutoff);
+  return sg_check_launch("sg_dlatents");
+}
+
+SG_EXPORT int sg_dlatents_bwd(const float* g, float* gw1, float* gw2, int B, int L, int D, int mix_cutoff, float psi,
+                              int trunc_cutoff, int has_trunc, void* stream) {
+  long long total = (long long)B * D;
+  dlatents_bwd_kernel<<<sg_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(g, gw1, gw2, B, L, D, mix_cutoff, psi, trunc_cutoff, has_trunc);
+  return sg_check_launch("sg_dlatents_bwd");
+}

@@ -1,0 +1,74 @@
+"""Data-parallel gradient exchange: one process per GPU, flat fp32 gradient buckets all-reduced over NCCL
+(NVLink 5 / NVSwitch) on a side stream, overlapped with the fused optimizer work of earlier buckets.
+
+The reference has no multi-GPU code at all (`# TODO` at models/GAN.py:509-510); semantics follow SURVEY.md 8(e):
+identical replicas, per-rank local batch, gradients averaged (sum then 1/world folded into the Adam kernel), rank-0
+broadcast of parameters and buffers at start.  Works with the gloo backend on CPU tensors for the host-logic tests."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def bucketize(sizes, bucket_elems):
+    """Greedy contiguous bucketing of tensor sizes -> list of lists of indices."""
+    buckets, cur, acc = [], [], 0
+    for i, n in enumerate(sizes):
+        if cur and acc + n > bucket_elems:
+            buckets.append(cur)
+            cur, acc = [], 0
+        cur.append(i)
+        acc += n
+    if cur:
+        buckets.append(cur)
+    return buckets
+
+
+class DataParallelContext:
+    def __init__(self, device, bucket_elems=8 * 1024 * 1024):
+        self.device = device
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.bucket_elems = bucket_elems
+        self.comm_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
+
+    @classmethod
+    def from_env(cls, device):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return cls(device)
+        return None
+
+    def broadcast_module(self, module, src=0):
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src)
+
+    def reduce_buckets(self, grads):
+        """grads: list of tensors (same device).  Returns (flats, placement) where flats are SUM-reduced flat
+        buckets and placement[i] = (bucket_index, offset).  All-reduces are issued asynchronously; the caller must
+        call `wait()` on each returned work handle (done in allreduce_grads)."""
+        sizes = [g.numel() for g in grads]
+        plan = bucketize(sizes, self.bucket_elems)
+        flats, works, placement = [], [], [None] * len(grads)
+        for b, idxs in enumerate(plan):
+            off = 0
+            for i in idxs:
+                placement[i] = (b, off)
+                off += sizes[i]
+            flat = torch.cat([grads[i].reshape(-1) for i in idxs])
+            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+            flats.append(flat)
+        return flats, works, placement
+
+    def allreduce_grads(self, optim):
+        """Average the gradients of `optim`'s parameters across ranks.  The 1/world scale is applied in place here
+        so that every downstream consumer (clip norm, Adam) sees averaged gradients."""
+        params = [p for g in optim.param_groups for p in g["params"] if p.grad is not None]
+        if not params:
+            return
+        grads = [p.grad for p in params]
+        flats, works, placement = self.reduce_buckets(grads)
+        for b, (flat, w) in enumerate(zip(flats, works)):
+            w.wait()
+            flat.mul_(1.0 / self.world)
+        for p, (b, off) in zip(params, placement):
+            p.grad = flats[b][off:off + p.numel()].view_as(p)

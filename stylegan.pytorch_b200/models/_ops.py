@@ -1,0 +1,900 @@
+"""torch.autograd.Function wrappers over the libsgb200 C-ABI.
+
+Activations are NHWC-contiguous tensors [N,H,W,C] in the engine dtype (fp32 or bf16); parameters, images and
+statistics are fp32.  Every Function on the discriminator path has a backward built from other Functions, so the R1
+gradient penalty (reference models/Losses.py:197-210, autograd.grad(create_graph=True)) differentiates through the
+backward pass without PyTorch having to see inside a kernel.  Generator-only Functions are once-differentiable.
+
+PyTorch is plumbing here: it owns memory, streams and the autograd tape; all arithmetic is in the kernels."""
+import ctypes
+import math
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _geom
+from ._lib import lib, ptr, stream, code, count_launch, F32
+
+_state = {"dtype": torch.float32, "use_tc": True}
+
+
+def set_precision(p):
+    """'fp32' (parity mode, CUDA-core kernels) or 'bf16' (tcgen05 tensor-core kernels, fp32 accumulation)."""
+    _state["dtype"] = {"fp32": torch.float32, "bf16": torch.bfloat16, torch.float32: torch.float32,
+                       torch.bfloat16: torch.bfloat16}[p]
+
+
+def precision():
+    return _state["dtype"]
+
+
+def set_use_tc(flag):
+    _state["use_tc"] = bool(flag)
+
+
+def _require_cuda(t):
+    if not t.is_cuda:
+        raise RuntimeError("sgb200: the StyleGAN hot path runs on CUDA tensors only (no CPU fallback); got a %s "
+                           "tensor" % t.device)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# weight preparation cache
+# ---------------------------------------------------------------------------------------------------------------
+_coef_cache = {}
+_prep_cache = {}
+
+
+def _coef_dev(kind, k, direction, device):
+    key = (kind, k, direction, device)
+    c = _coef_cache.get(key)
+    if c is None:
+        c = torch.from_numpy(_geom.tables(kind, k, direction)["coef"]).to(device).contiguous()
+        _coef_cache[key] = c
+    return c
+
+
+def prepped_weight(W, kind, direction, dtype, scale):
+    """Effective weights E[npt][A][B] in `dtype`.  Cached for nn.Parameters only, keyed on (storage, version,
+    weights epoch): the fused optimizer writes parameters through raw pointers and bumps the epoch instead of the
+    tensor version.  Code that edits `param.data` behind autograd's back must call clear_weight_cache()."""
+    Wd = W.detach()
+    co, ci, k, _ = W.shape
+    cacheable = isinstance(W, torch.nn.Parameter)
+    sub = (kind, direction, dtype, float(scale))
+    if cacheable:
+        key = (Wd.data_ptr(), W._version, _epoch[0], tuple(W.shape))
+        hit = _prep_cache.get(id(W))
+        if hit is not None and hit[0] == key:
+            E = hit[1].get(sub)
+            if E is not None:
+                return E
+        else:
+            if len(_prep_cache) > 2048:
+                _prep_cache.clear()
+            hit = (key, {})
+            _prep_cache[id(W)] = hit
+    t = _geom.tables(kind, k, direction)
+    npt = t["nphase"] * t["ntaps"]
+    a, b = (co, ci) if t["transpose"] else (ci, co)
+    E = torch.empty((npt, a, b), dtype=dtype, device=W.device)
+    coef = _coef_dev(kind, k, direction, W.device)
+    lib.sg_wprep_fwd(ptr(_c(Wd)), ptr(E), code(dtype), co, ci, k * k, npt, ptr(coef), float(scale), t["transpose"],
+                     stream())
+    count_launch()
+    if cacheable:
+        hit[1][sub] = E
+    return E
+
+
+_epoch = [0]
+
+
+def bump_weights_epoch():
+    """Called by the fused optimizer after it has rewritten parameters in place."""
+    _epoch[0] += 1
+
+
+def clear_weight_cache():
+    _prep_cache.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense convolutions
+# ---------------------------------------------------------------------------------------------------------------
+def _conv_raw(x, W, kind, direction, scale, bias=None, bias_mul=1.0, act=False):
+    _require_cuda(x)
+    x = _c(x)
+    co, ci, k, _ = W.shape
+    N, H, Wd, C = x.shape
+    cin, cout = (ci, co) if direction == "fwd" else (co, ci)
+    assert C == cin, "channel mismatch: activation has %d, weight expects %d" % (C, cin)
+    Ho, Wo = _geom.out_hw(kind, direction, H, Wd)
+    y = torch.empty((N, Ho, Wo, cout), dtype=x.dtype, device=x.device)
+    from . import _tc
+    if _tc.try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
+        return y
+    E = prepped_weight(W, kind, direction, x.dtype, scale)
+    g = _geom.make_geom(kind, k, direction, N, H, Wd, cin, cout)
+    lib.sg_conv_generic(ptr(x), ptr(E), ptr(y), ptr(bias), float(bias_mul), int(act), code(x.dtype),
+                        ctypes.addressof(g), stream())
+    count_launch()
+    return y
+
+
+class Conv(Function):
+    """y = conv_{kind,direction}(x; scale*W).  direction 'dgrad' is the adjoint map (used by backward and by R1)."""
+
+    @staticmethod
+    def forward(ctx, x, W, kind, direction, scale):
+        ctx.save_for_backward(x, W)
+        ctx.cfg = (kind, direction, scale)
+        return _conv_raw(x, W, kind, direction, scale)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        kind, direction, scale = ctx.cfg
+        gx = gW = None
+        if ctx.needs_input_grad[0]:
+            gx = Conv.apply(gy, W, kind, "dgrad" if direction == "fwd" else "fwd", scale)
+        if ctx.needs_input_grad[1]:
+            gW = ConvWgrad.apply(x, gy, kind, scale, W.shape) if direction == "fwd" else \
+                ConvWgrad.apply(gy, x, kind, scale, W.shape)
+        return gx, gW, None, None, None
+
+
+class ConvWgrad(Function):
+    """dW = scale * wgrad(x_like, dy_like) for the layer's forward geometry (bilinear in its two inputs)."""
+
+    @staticmethod
+    def forward(ctx, xl, dyl, kind, scale, wshape):
+        _require_cuda(xl)
+        xl, dyl = _c(xl), _c(dyl)
+        co, ci, k, _ = wshape
+        N, H, Wd, C = xl.shape
+        assert C == ci and dyl.shape[-1] == co
+        g = _geom.make_geom(kind, k, "fwd", N, H, Wd, ci, co)
+        assert tuple(dyl.shape[1:3]) == (g.Hout, g.Wout)
+        t = _geom.tables(kind, k, "fwd")
+        npt = t["nphase"] * t["ntaps"]
+        dW = torch.empty(wshape, dtype=torch.float32, device=xl.device)
+        from . import _tc
+        if not _tc.try_wgrad(xl, dyl, kind, scale, dW):
+            ns = lib.sg_wgrad_splits(ctypes.addressof(g))
+            part = torch.empty((ns, npt, ci, co), dtype=torch.float32, device=xl.device)
+            lib.sg_wgrad_generic(ptr(xl), ptr(dyl), ptr(part), ns, code(xl.dtype), ctypes.addressof(g), stream())
+            coef = _coef_dev(kind, k, "fwd", xl.device)
+            lib.sg_wprep_bwd(ptr(part), ns, ptr(dW), co, ci, k * k, npt, ptr(coef), float(scale), 0, 0, stream())
+            count_launch(2)
+        ctx.save_for_backward(xl, dyl)
+        ctx.cfg = (kind, scale)
+        return dW
+
+    @staticmethod
+    def backward(ctx, ggW):
+        xl, dyl = ctx.saved_tensors
+        kind, scale = ctx.cfg
+        ggW = _c(ggW)
+        gx = Conv.apply(dyl, ggW, kind, "dgrad", scale) if ctx.needs_input_grad[0] else None
+        gd = Conv.apply(xl, ggW, kind, "fwd", scale) if ctx.needs_input_grad[1] else None
+        return gx, gd, None, None, None
+
+
+class ConvBiasAct(Function):
+    """y = [lrelu](conv(x; scale*W) + bias*bias_mul) with bias/activation fused into the conv epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, kind, scale, bias_mul, act):
+        y = _conv_raw(x, W, kind, "fwd", scale, bias, bias_mul, act)
+        ctx.save_for_backward(x, W, y if act else None)
+        ctx.cfg = (kind, scale, bias_mul, act, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        kind, scale, bias_mul, act, has_bias = ctx.cfg
+        g = LreluBwd.apply(gy, y) if act else gy
+        gx = Conv.apply(g, W, kind, "dgrad", scale) if ctx.needs_input_grad[0] else None
+        gW = ConvWgrad.apply(x, g, kind, scale, W.shape) if ctx.needs_input_grad[1] else None
+        gb = None
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1)
+        return gx, gW, gb, None, None, None, None
+
+
+class LreluBwd(Function):
+    """gx = g * lrelu'(ref): linear in g, piecewise constant in ref."""
+
+    @staticmethod
+    def forward(ctx, g, ref):
+        _require_cuda(g)
+        g, ref = _c(g), _c(ref)
+        assert g.dtype == ref.dtype and g.shape == ref.shape
+        out = torch.empty_like(g)
+        lib.sg_lrelu_bwd(ptr(g), ptr(ref), ptr(out), g.numel(), code(g.dtype), stream())
+        count_launch()
+        ctx.save_for_backward(ref)
+        return out
+
+    @staticmethod
+    def backward(ctx, gg):
+        (ref,) = ctx.saved_tensors
+        return LreluBwd.apply(gg, ref), None
+
+
+class ChannelSum(Function):
+    """rows[j][c] = scale * sum_p wt_j(p) x[p][c] (+ an all-ones row).  x NHWC, wt fp32 [N,J,H,W] or None."""
+
+    @staticmethod
+    def forward(ctx, x, wt, ones, scale):
+        _require_cuda(x)
+        x = _c(x)
+        N = x.shape[0]
+        C = x.shape[-1]
+        P = x.numel() // C
+        HW = P // N
+        J = 0
+        if wt is not None:
+            wt = _c(wt.float())
+            J = wt.numel() // P
+        rows = J + (1 if ones else 0)
+        out = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+        nblk = lib.sg_channel_sum_blocks(P)
+        ws = torch.empty((nblk, rows, C), dtype=torch.float32, device=x.device)
+        lib.sg_channel_sum(ptr(x), code(x.dtype), ptr(wt), J, int(bool(ones)), P, HW, C, ptr(ws), ptr(out),
+                           float(scale), 0, stream())
+        count_launch(2)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        raise RuntimeError("sgb200: ChannelSum is a leaf gradient reduction and is not differentiable")
+
+
+class Blur(Function):
+    """Depthwise [1,2,1]^2/16 blur (+ optional per-channel bias)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, bias_mul):
+        _require_cuda(x)
+        x = _c(x)
+        N, H, W, C = x.shape
+        y = torch.empty_like(x)
+        lib.sg_blur3(ptr(x), ptr(y), ptr(bias), float(bias_mul), code(x.dtype), N, H, W, C, stream())
+        count_launch()
+        ctx.cfg = (bias is not None, bias_mul)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        has_bias, bias_mul = ctx.cfg
+        gx = Blur.apply(g, None, 1.0) if ctx.needs_input_grad[0] else None
+        gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1) if (has_bias and ctx.needs_input_grad[1]) else None
+        return gx, gb, None
+
+
+class Axpby(Function):
+    """a*x + b*y (y optional)."""
+
+    @staticmethod
+    def forward(ctx, x, y, a, b):
+        _require_cuda(x)
+        x = _c(x)
+        if y is not None:
+            y = _c(y)
+            assert y.shape == x.shape and y.dtype == x.dtype
+        out = torch.empty_like(x)
+        lib.sg_axpby(ptr(x), ptr(y), ptr(out), float(a), float(b), x.numel(), code(x.dtype), stream())
+        count_launch()
+        ctx.cfg = (a, b, y is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, has_y = ctx.cfg
+        gx = Axpby.apply(g, None, a, 0.0) if ctx.needs_input_grad[0] else None
+        gy = Axpby.apply(g, None, b, 0.0) if (has_y and ctx.needs_input_grad[1]) else None
+        return gx, gy, None, None
+
+
+class Cast(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        _require_cuda(x)
+        x = _c(x)
+        ctx.src = x.dtype
+        if x.dtype == dtype:
+            return x.view_as(x)
+        y = torch.empty(x.shape, dtype=dtype, device=x.device)
+        lib.sg_cast(ptr(x), code(x.dtype), ptr(y), code(dtype), x.numel(), stream())
+        count_launch()
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return Cast.apply(g, ctx.src), None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# from_rgb / image helpers (discriminator side: double-differentiable)
+# ---------------------------------------------------------------------------------------------------------------
+class RgbIn(Function):
+    """y[N,H,W,C] = [lrelu](scale * W[C,K] img[N,K,H,W] + bias*bias_mul);  img fp32 NCHW."""
+
+    @staticmethod
+    def forward(ctx, img, W, bias, scale, bias_mul, act, dtype):
+        _require_cuda(img)
+        img = _c(img.float())
+        N, K, H, Wd = img.shape
+        C = W.shape[0]
+        Wm = _c(W.detach().reshape(C, K))
+        y = torch.empty((N, H, Wd, C), dtype=dtype, device=img.device)
+        lib.sg_rgb_in(ptr(img), ptr(Wm), ptr(bias), float(scale), float(bias_mul), int(act), ptr(y), code(dtype),
+                      N, H * Wd, K, C, stream())
+        count_launch()
+        ctx.save_for_backward(img, W, y if act else None)
+        ctx.cfg = (scale, bias_mul, act, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        img, W, y = ctx.saved_tensors
+        scale, bias_mul, act, has_bias = ctx.cfg
+        g = LreluBwd.apply(gy, y) if act else gy
+        gimg = RgbInDgrad.apply(g, W, scale) if ctx.needs_input_grad[0] else None
+        gW = gb = None
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            rows = ChannelSum.apply(g, img, True, 1.0)           # [K+1, C]
+            K = img.shape[1]
+            if ctx.needs_input_grad[1]:
+                gW = (rows[:K].t() * scale).reshape(W.shape)
+            if has_bias and ctx.needs_input_grad[2]:
+                gb = rows[K] * bias_mul
+        return gimg, gW, gb, None, None, None, None
+
+
+class RgbInDgrad(Function):
+    """gimg[N,K,H,W] = scale * W^T g  (adjoint of RgbIn wrt the image)."""
+
+    @staticmethod
+    def forward(ctx, g, W, scale):
+        _require_cuda(g)
+        g = _c(g)
+        N, H, Wd, C = g.shape
+        K = W.shape[1]
+        Wm = _c(W.detach().reshape(C, K))
+        gimg = torch.empty((N, K, H, Wd), dtype=torch.float32, device=g.device)
+        lib.sg_rgb_in_dgrad(ptr(g), code(g.dtype), ptr(Wm), float(scale), ptr(gimg), N, H * Wd, K, C, stream())
+        count_launch()
+        ctx.save_for_backward(g, W)
+        ctx.scale = scale
+        return gimg
+
+    @staticmethod
+    def backward(ctx, t):
+        g, W = ctx.saved_tensors
+        scale = ctx.scale
+        cg = RgbIn.apply(t, W, None, scale, 1.0, False, g.dtype) if ctx.needs_input_grad[0] else None
+        cW = None
+        if ctx.needs_input_grad[1]:
+            rows = ChannelSum.apply(g, t, False, scale)           # [K, C]
+            cW = rows.t().reshape(W.shape)
+        return cg, cW, None
+
+
+class PoolNCHW(Function):
+    """fp32 NCHW box filter: out = scale * sum over fxf blocks (scale=1/f^2 -> AvgPool2d(f))."""
+
+    @staticmethod
+    def forward(ctx, x, f, scale):
+        _require_cuda(x)
+        x = _c(x.float())
+        N, K, H, W = x.shape
+        out = torch.empty((N, K, H // f, W // f), dtype=torch.float32, device=x.device)
+        lib.sg_pool_nchw(ptr(x), ptr(out), N * K, H // f, W // f, f, float(scale), stream())
+        count_launch()
+        ctx.cfg = (f, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f, scale = ctx.cfg
+        return UpsampleNCHW.apply(g, f, scale), None, None
+
+
+class UpsampleNCHW(Function):
+    """fp32 NCHW nearest up-sampling by f, times scale."""
+
+    @staticmethod
+    def forward(ctx, x, f, scale):
+        _require_cuda(x)
+        x = _c(x.float())
+        N, K, H, W = x.shape
+        out = torch.empty((N, K, H * f, W * f), dtype=torch.float32, device=x.device)
+        lib.sg_upsample_nchw(ptr(x), ptr(out), N * K, H, W, f, float(scale), stream())
+        count_launch()
+        ctx.cfg = (f, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f, scale = ctx.cfg
+        return PoolNCHW.apply(g, f, scale), None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense layers (fp32)
+# ---------------------------------------------------------------------------------------------------------------
+def _rows(x):
+    """2-D fp32 view with unit inner stride -> (tensor, ldx)."""
+    assert x.dim() == 2 and x.dtype == torch.float32
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    return x, (x.stride(0) if x.shape[0] > 1 else x.shape[1])
+
+
+class Linear(Function):
+    """y = [lrelu](scale * x W^T + bias*bias_mul), fp32."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, scale, bias_mul, act):
+        _require_cuda(x)
+        x, ldx = _rows(x)
+        B, I = x.shape
+        O = W.shape[0]
+        y = torch.empty((B, O), dtype=torch.float32, device=x.device)
+        lib.sg_linear_fwd(ptr(x), ldx, ptr(_c(W.detach())), ptr(bias), float(scale), float(bias_mul), int(act),
+                          ptr(y), B, I, O, stream())
+        count_launch()
+        ctx.save_for_backward(x, W, y if act else None)
+        ctx.cfg = (scale, bias_mul, act, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        scale, bias_mul, act, has_bias = ctx.cfg
+        g = LreluBwd.apply(gy, y) if act else gy
+        gx = LinearDgrad.apply(g, W, scale) if ctx.needs_input_grad[0] else None
+        gW = gb = None
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            gW, gb = LinearWgrad.apply(g, x, scale, bias_mul, has_bias)
+        return gx, gW, (gb if has_bias else None), None, None, None
+
+
+class LinearDgrad(Function):
+    @staticmethod
+    def forward(ctx, gy, W, scale):
+        _require_cuda(gy)
+        gy = _c(gy)
+        B, O = gy.shape
+        I = W.shape[1]
+        gx = torch.empty((B, I), dtype=torch.float32, device=gy.device)
+        lib.sg_linear_dgrad(ptr(gy), ptr(_c(W.detach())), float(scale), ptr(gx), B, I, O, stream())
+        count_launch()
+        ctx.save_for_backward(gy, W)
+        ctx.scale = scale
+        return gx
+
+    @staticmethod
+    def backward(ctx, t):
+        gy, W = ctx.saved_tensors
+        scale = ctx.scale
+        cg = Linear.apply(t, W, None, scale, 1.0, False) if ctx.needs_input_grad[0] else None
+        cW = LinearWgrad.apply(gy, t, scale, 1.0, False)[0] if ctx.needs_input_grad[1] else None
+        return cg, cW, None
+
+
+class LinearWgrad(Function):
+    @staticmethod
+    def forward(ctx, gy, x, scale, bias_mul, want_bias):
+        _require_cuda(gy)
+        gy = _c(gy)
+        x, ldx = _rows(x)
+        B, O = gy.shape
+        I = x.shape[1]
+        gW = torch.empty((O, I), dtype=torch.float32, device=gy.device)
+        gb = torch.empty((O,), dtype=torch.float32, device=gy.device) if want_bias else None
+        lib.sg_linear_wgrad(ptr(gy), ptr(x), ldx, float(scale), float(bias_mul), ptr(gW), ptr(gb), B, I, O, 0,
+                            stream())
+        count_launch(2 if want_bias else 1)
+        ctx.mark_non_differentiable(gW)
+        if gb is None:
+            gb = torch.empty((0,), dtype=torch.float32, device=gy.device)
+        ctx.mark_non_differentiable(gb)
+        return gW, gb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, a, b):
+        raise RuntimeError("sgb200: LinearWgrad is not differentiable")
+
+
+class PixelNorm(Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        _require_cuda(x)
+        x = _c(x.float())
+        y = torch.empty_like(x)
+        lib.sg_pixelnorm_fwd(ptr(x), ptr(y), x.shape[0], x.shape[1], float(eps), stream())
+        count_launch()
+        ctx.save_for_backward(x)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        lib.sg_pixelnorm_bwd(ptr(_c(g)), ptr(x), ptr(gx), x.shape[0], x.shape[1], float(ctx.eps), stream())
+        count_launch()
+        return gx, None
+
+
+class MbStd(Function):
+    """MinibatchStdDev on fp32 NHWC [B,H,W,C] -> [B,H,W,C+1]."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        _require_cuda(x)
+        x = _c(x)
+        assert x.dtype == torch.float32
+        B, H, W, C = x.shape
+        G = min(group, B)
+        out = torch.empty((B, H, W, C + 1), dtype=torch.float32, device=x.device)
+        ws = torch.empty((2 * (B // G) + 2,), dtype=torch.float32, device=x.device)
+        lib.sg_mbstd_fwd(ptr(x), ptr(out), ptr(ws), B, H * W, C, G, stream())
+        count_launch(2)
+        ctx.save_for_backward(x)
+        ctx.G = G
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        return MbStdBwd.apply(gout, x, ctx.G), None
+
+
+class MbStdBwd(Function):
+    @staticmethod
+    def forward(ctx, gout, x, G):
+        gout = _c(gout)
+        B, H, W, C = x.shape
+        gx = torch.empty_like(x)
+        ws = torch.empty((2 * (B // G) + 2,), dtype=torch.float32, device=x.device)
+        lib.sg_mbstd_bwd(ptr(gout), ptr(x), ptr(gx), ptr(ws), B, H * W, C, G, stream())
+        count_launch(2)
+        ctx.save_for_backward(gout, x)
+        ctx.G = G
+        return gx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, t):
+        gout, x = ctx.saved_tensors
+        t = _c(t)
+        B, H, W, C = x.shape
+        G = ctx.G
+        cg = torch.empty_like(gout)
+        cx = torch.empty_like(x)
+        ws = torch.empty((2 * (B // G) + 2,), dtype=torch.float32, device=x.device)
+        lib.sg_mbstd_bwd2(ptr(t), ptr(gout), ptr(x), ptr(cg), ptr(cx), ptr(ws), B, H * W, C, G, stream())
+        count_launch(3)
+        return cg, cx, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------------------
+class SoftplusMean(Function):
+    """mean(softplus(sign * x)) as a 1-element fp32 tensor."""
+
+    @staticmethod
+    def forward(ctx, x, sign):
+        _require_cuda(x)
+        x = _c(x.float())
+        n = x.numel()
+        out = torch.empty((1,), dtype=torch.float32, device=x.device)
+        lib.sg_softplus_sum(ptr(x), n, float(sign), 1.0 / n, ptr(out), 0, stream())
+        count_launch()
+        ctx.save_for_backward(x)
+        ctx.sign = sign
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        n = x.numel()
+        gx = torch.empty_like(x)
+        lib.sg_softplus_bwd(ptr(x), n, float(ctx.sign), ptr(_c(g.float())), 1.0 / n, ptr(gx), stream())
+        count_launch()
+        return gx, None
+
+
+class SqSum(Function):
+    """scale * sum(x^2) as a 1-element fp32 tensor (R1 penalty, Losses.py:209)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        _require_cuda(x)
+        x = _c(x.float())
+        out = torch.empty((1,), dtype=torch.float32, device=x.device)
+        ws = torch.empty((1024,), dtype=torch.float64, device=x.device)
+        lib.sg_sqsum(ptr(x), x.numel(), float(scale), ptr(out), 0, ptr(ws), stream())
+        count_launch(2)
+        ctx.save_for_backward(x)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        lib.sg_scale_by_scalar(ptr(x), ptr(_c(g.float())), 2.0 * ctx.scale, ptr(gx), x.numel(), stream())
+        count_launch()
+        return gx, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# generator-only fused Functions (once-differentiable)
+# ---------------------------------------------------------------------------------------------------------------
+class Epilogue(Function):
+    """LayerEpilogue: out = StyleMod(InstanceNorm(lrelu(y + bias*bmul + noise_w*noise)), style).
+    y NHWC; bias [C] or None; noise fp32 [N,1,H,W] or None; noise_w [C]; style fp32 [N,2C] or None."""
+
+    @staticmethod
+    def forward(ctx, y, bias, bias_mul, noise, noise_w, style, eps, act=True):
+        _require_cuda(y)
+        y = _c(y)
+        N, H, W, C = y.shape
+        HW = H * W
+        dev = y.device
+        if noise is not None:
+            noise = _c(noise.float())
+            assert noise.numel() == N * HW, "noise must be [N,1,H,W]"
+        if style is not None:
+            style = _c(style)
+        z = torch.empty_like(y)
+        sums = torch.zeros((N, C, 2), dtype=torch.float64, device=dev)
+        lib.sg_epi_act_stats(ptr(y), ptr(bias), float(bias_mul), ptr(noise), ptr(noise_w if noise is not None else None),
+                             int(act), ptr(z), ptr(sums), code(y.dtype), N, HW, C, stream())
+        mr = torch.empty((N, C, 2), dtype=torch.float32, device=dev)
+        ab = torch.empty((N, C, 2), dtype=torch.float32, device=dev)
+        lib.sg_epi_finalize(ptr(sums), ptr(style), ptr(mr), ptr(ab), N, C, HW, float(eps), stream())
+        out = torch.empty_like(y)
+        lib.sg_affine_nc(ptr(z), ptr(ab), ptr(out), code(y.dtype), N, HW, C, stream())
+        count_launch(4)
+        ctx.save_for_backward(z, mr, style, noise)
+        ctx.cfg = (bias is not None, bias_mul, noise is not None, act)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        z, mr, style, noise = ctx.saved_tensors
+        has_bias, bias_mul, has_noise, act = ctx.cfg
+        g = _c(g)
+        N, H, W, C = z.shape
+        HW = H * W
+        dev = z.device
+        sums = torch.zeros((N, C, 2), dtype=torch.float64, device=dev)
+        lib.sg_epi_bwd_reduce(ptr(g), ptr(z), ptr(mr), ptr(sums), code(z.dtype), N, HW, C, stream())
+        gstyle = torch.empty((N, 2 * C), dtype=torch.float32, device=dev) if style is not None else None
+        coef = torch.empty((N, C, 3), dtype=torch.float32, device=dev)
+        lib.sg_epi_bwd_finalize(ptr(sums), ptr(mr), ptr(style), ptr(gstyle), ptr(coef), N, C, HW, stream())
+        gy = torch.empty_like(z)
+        lib.sg_epi_bwd_apply(ptr(g), ptr(z), ptr(coef), int(act), ptr(gy), code(z.dtype), N, HW, C, stream())
+        count_launch(4)
+        gb = gnw = None
+        need_b = has_bias and ctx.needs_input_grad[1]
+        need_n = has_noise and ctx.needs_input_grad[4]
+        if need_b or need_n:
+            rows = ChannelSum.apply(gy, noise if need_n else None, need_b, 1.0)
+            if need_n:
+                gnw = rows[0]
+            if need_b:
+                gb = rows[-1] * bias_mul
+        return gy, gb, None, None, gnw, gstyle, None, None
+
+
+class ToRgb(Function):
+    """Fused to_rgb + fade-in (reference GAN.py:199-204):
+        out[N,K,H,W] fp32 = a_hi * rgb(x_hi; W_hi, b_hi) + a_lo * rgb(nearest_up2(x_lo); W_lo, b_lo)
+    x_lo/W_lo/b_lo may be None (depth 0 / 'fixed')."""
+
+    @staticmethod
+    def forward(ctx, x_hi, W_hi, b_hi, s_hi, a_hi, x_lo, W_lo, b_lo, s_lo, a_lo):
+        _require_cuda(x_hi)
+        x_hi = _c(x_hi)
+        N, H, W, C = x_hi.shape
+        K = W_hi.shape[0]
+        out = torch.empty((N, K, H, W), dtype=torch.float32, device=x_hi.device)
+        Wh = _c(W_hi.detach().reshape(K, C))
+        lib.sg_rgb_out(ptr(x_hi), code(x_hi.dtype), ptr(Wh), ptr(b_hi), float(s_hi), 1.0, float(a_hi), 0.0, ptr(out),
+                       N, H, W, C, K, 1, stream())
+        count_launch()
+        if x_lo is not None:
+            x_lo = _c(x_lo)
+            Cl = x_lo.shape[-1]
+            Wl = _c(W_lo.detach().reshape(K, Cl))
+            lib.sg_rgb_out(ptr(x_lo), code(x_lo.dtype), ptr(Wl), ptr(b_lo), float(s_lo), 1.0, float(a_lo), 1.0,
+                           ptr(out), N, H // 2, W // 2, Cl, K, 2, stream())
+            count_launch()
+        ctx.save_for_backward(x_hi, W_hi, x_lo, W_lo)
+        ctx.cfg = (s_hi, a_hi, s_lo, a_lo, b_hi is not None, b_lo is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x_hi, W_hi, x_lo, W_lo = ctx.saved_tensors
+        s_hi, a_hi, s_lo, a_lo, hb_hi, hb_lo = ctx.cfg
+        g = _c(g.float())
+        N, H, W, C = x_hi.shape
+        K = W_hi.shape[0]
+        dev = g.device
+        st = stream()
+        res = [None] * 10
+        Wh = _c(W_hi.detach().reshape(K, C))
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x_hi)
+            lib.sg_rgb_out_dgrad(ptr(g), ptr(Wh), float(a_hi * s_hi), ptr(gx), code(x_hi.dtype), N, H, W, C, K, 1, st)
+            count_launch()
+            res[0] = gx
+        if ctx.needs_input_grad[1]:
+            res[1] = ChannelSum.apply(x_hi, g, False, a_hi * s_hi).reshape(W_hi.shape)
+        if hb_hi and ctx.needs_input_grad[2]:
+            gb = torch.empty((K,), dtype=torch.float32, device=dev)
+            lib.sg_plane_sum(ptr(g), ptr(gb), N, K, H * W, float(a_hi), 0, st)
+            count_launch()
+            res[2] = gb
+        if x_lo is not None:
+            Cl = x_lo.shape[-1]
+            Wl = _c(W_lo.detach().reshape(K, Cl))
+            if ctx.needs_input_grad[5]:
+                gx = torch.empty_like(x_lo)
+                lib.sg_rgb_out_dgrad(ptr(g), ptr(Wl), float(a_lo * s_lo), ptr(gx), code(x_lo.dtype), N, H // 2, W // 2,
+                                     Cl, K, 2, st)
+                count_launch()
+                res[5] = gx
+            if ctx.needs_input_grad[6]:
+                glo = torch.empty((N, K, H // 2, W // 2), dtype=torch.float32, device=dev)
+                lib.sg_pool_nchw(ptr(g), ptr(glo), N * K, H // 2, W // 2, 2, 1.0, st)
+                count_launch()
+                res[6] = ChannelSum.apply(x_lo, glo, False, a_lo * s_lo).reshape(W_lo.shape)
+            if hb_lo and ctx.needs_input_grad[7]:
+                gb = torch.empty((K,), dtype=torch.float32, device=dev)
+                lib.sg_plane_sum(ptr(g), ptr(gb), N, K, H * W, float(a_lo), 0, st)
+                count_launch()
+                res[7] = gb
+        return tuple(res)
+
+
+class Dlatents(Function):
+    """[B,L,D] dlatents from w1 (and w2 for style mixing) with truncation towards avg."""
+
+    @staticmethod
+    def forward(ctx, w1, w2, avg, L, mix_cutoff, psi, trunc_cutoff):
+        _require_cuda(w1)
+        w1 = _c(w1)
+        B, D = w1.shape
+        out = torch.empty((B, L, D), dtype=torch.float32, device=w1.device)
+        lib.sg_dlatents(ptr(w1), ptr(_c(w2) if w2 is not None else None), ptr(avg), ptr(out), B, L, D,
+                        int(mix_cutoff), float(psi), int(trunc_cutoff), stream())
+        count_launch()
+        ctx.cfg = (L, mix_cutoff, psi, trunc_cutoff, w2 is not None, avg is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        L, mix_cutoff, psi, trunc_cutoff, has2, has_trunc = ctx.cfg
+        g = _c(g)
+        B, _, D = g.shape
+        g1 = torch.empty((B, D), dtype=torch.float32, device=g.device)
+        g2 = torch.empty((B, D), dtype=torch.float32, device=g.device) if has2 else None
+        lib.sg_dlatents_bwd(ptr(g), ptr(g1), ptr(g2), B, L, D, int(mix_cutoff), float(psi), int(trunc_cutoff),
+                            int(has_trunc), stream())
+        count_launch()
+        return g1, g2, None, None, None, None, None
+
+
+def randn_device(shape, device, seed, offset):
+    """N(0,1) fp32 noise from the engine's Philox generator (NoiseLayer, CustomLayers.py:193)."""
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    lib.sg_randn(ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), int(offset), stream())
+    count_launch()
+    return out
+
+
+def he_scale(fan_in, gain, lrmul=1.0):
+    return gain * fan_in ** (-0.5) * lrmul
+
+
+class BiasNoise(Function):
+    """y = x + bias*bias_mul + noise_w*noise (stand-alone NoiseLayer / bias add)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, bias_mul, noise, noise_w, act=False):
+        _require_cuda(x)
+        x = _c(x)
+        C = x.shape[-1]
+        P = x.numel() // C
+        if noise is not None:
+            noise = _c(noise.float())
+            assert noise.numel() == P
+        y = torch.empty_like(x)
+        lib.sg_bias_noise(ptr(x), ptr(bias), float(bias_mul), ptr(noise), ptr(noise_w if noise is not None else None),
+                          int(act), ptr(y), code(x.dtype), P, C, stream())
+        count_launch()
+        ctx.save_for_backward(noise, y if act else None)
+        ctx.cfg = (bias is not None, bias_mul, noise is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        noise, y = ctx.saved_tensors
+        has_bias, bias_mul, has_noise = ctx.cfg
+        if y is not None:
+            g = LreluBwd.apply(g, y)
+        gb = gnw = None
+        need_b = has_bias and ctx.needs_input_grad[1]
+        need_n = has_noise and ctx.needs_input_grad[4]
+        if need_b or need_n:
+            rows = ChannelSum.apply(g, noise if need_n else None, need_b, 1.0)
+            if need_n:
+                gnw = rows[0]
+            if need_b:
+                gb = rows[-1] * bias_mul
+        return g, gb, None, None, gnw, None
+
+
+class AffineNC(Function):
+    """out[n,p,c] = ab[n,c,0]*x + ab[n,c,1] (stand-alone StyleMod / InstanceNorm application)."""
+
+    @staticmethod
+    def forward(ctx, x, ab):
+        _require_cuda(x)
+        x = _c(x)
+        ab = _c(ab.float())
+        N, C = x.shape[0], x.shape[-1]
+        HW = x.numel() // (N * C)
+        out = torch.empty_like(x)
+        lib.sg_affine_nc(ptr(x), ptr(ab), ptr(out), code(x.dtype), N, HW, C, stream())
+        count_launch()
+        ctx.save_for_backward(x, ab)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, ab = ctx.saved_tensors
+        g = _c(g)
+        N, C = x.shape[0], x.shape[-1]
+        HW = x.numel() // (N * C)
+        dev = x.device
+        gx = gab = None
+        if ctx.needs_input_grad[0]:
+            a0 = torch.stack([ab[..., 0], torch.zeros_like(ab[..., 0])], dim=-1).contiguous()
+            gx = torch.empty_like(x)
+            lib.sg_affine_nc(ptr(g), ptr(a0), ptr(gx), code(x.dtype), N, HW, C, stream())
+            count_launch()
+        if ctx.needs_input_grad[1]:
+            sums = torch.zeros((N, C, 2), dtype=torch.float64, device=dev)
+            mr = torch.zeros((N, C, 2), dtype=torch.float32, device=dev)
+            mr[..., 1] = 1.0
+            lib.sg_epi_bwd_reduce(ptr(g), ptr(x), ptr(mr), ptr(sums), code(x.dtype), N, HW, C, stream())
+            count_launch()
+            gab = torch.stack([sums[..., 1], sums[..., 0]], dim=-1).float()   # d/da = sum g*x, d/db = sum g
+        return gx, gab

@@ -1,11 +1,369 @@
-// tcgen05 / TMA implicit-GEMM convolution (placeholder until the kernel lands in this file).
+// tcgen05 / TMA implicit-GEMM 3x3 stride-1 convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+//   y[n,h,w,co] = act( sum_{kh,kw,ci} x[n,h+kh-1,w+kw-1,ci] * E[kh*3+kw][co][ci] + bias[co]*bias_mul )
+//
+// reference call site: EqualizedConv2d.forward -> F.conv2d(x, W*w_mul, bias, padding=1), models/CustomLayers.py:170-171
+// (and, with flipped/transposed E, its dgrad).  No im2col: for each of the three horizontal shifts kw one TMA box
+// {64 ch, TW px, TH+2 rows} of the NHWC activation lands in 128B-swizzled shared memory (out-of-bounds rows/columns
+// are zero-filled by TMA = the conv padding); the three vertical taps kh are UMMA descriptors that start kh*TW rows
+// into that same buffer, so every activation byte is fetched 3*(TH+2)/TH = 3.75x from L2 instead of 9x.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue (TMEM -> regs -> bias,
+// LeakyReLU -> bf16 -> global).  Persistent over output tiles of TH x TW = 128 pixels x BN channels, double-buffered
+// TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "sg_common.cuh"
 #include "../../include/sgb200.h"
+#include <cuda.h>
+#include <mutex>
 
-SG_EXPORT int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout) { return 0; }
+namespace tc {
+
+constexpr int TH = 8, TW = 16, BK = 64;
+constexpr int HALO_ROWS = (TH + 2) * TW;           // 160 smem rows of 128 B per kw-shift
+constexpr int A_BYTES = HALO_ROWS * BK * 2;        // 20480
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+struct __align__(8) Barriers {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug traps (context error, reported by the next CUDA call) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address  [0,14)
+  d |= (uint64_t)(1024u >> 4) << 32;              // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                         // layout: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+  int N, H, W, Cin, Cout, BN;
+  int tiles_h, tiles_w, tiles_n, num_tiles;
+  int kchunks, stages, stage_bytes, tmem_cols;
+  const float* bias;
+  float bias_mul;
+  int act;
+  __nv_bfloat16* y;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)p.stages * p.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_w);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int b_tap_bytes = p.BN * BK * 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int nt = tile % p.tiles_n;
+        int r = tile / p.tiles_n;
+        int wt = r % p.tiles_w; r /= p.tiles_w;
+        int ht = r % p.tiles_h;
+        int n = r / p.tiles_h;
+        const int h0 = ht * TH, w0 = wt * TW, n0 = nt * p.BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
+            uint8_t* sB = sA + A_BYTES;
+            mbar_expect_tx(&bars->full[stage], (uint32_t)(A_BYTES + 3 * b_tap_bytes));
+            tma_load_4d(sA, &map_x, &bars->full[stage], kc * BK, w0 + kw - 1, h0 - 1, n);
+            for (int kh = 0; kh < 3; ++kh)
+              tma_load_2d(sB + kh * b_tap_bytes, &map_w, &bars->full[stage], kc * BK, (kh * 3 + kw) * p.Cout + n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+        uint32_t first = 1;
+        for (int it = 0; it < p.kchunks * 3; ++it) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              uint64_t ad = make_desc_sw128(sA + kh * (TW * 128) + k * 32);
+              uint64_t bd = make_desc_sw128(sB + kh * b_tap_bytes + k * 32);
+              umma_bf16(tmem_d, ad, bd, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+          umma_commit(&bars->empty[stage]);          // frees the smem stage once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->tmem_full[acc]);           // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int pr = m / TW, pc = m % TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int nt = tile % p.tiles_n;
+      int r = tile / p.tiles_n;
+      int wt = r % p.tiles_w; r /= p.tiles_w;
+      int ht = r % p.tiles_h;
+      int n = r / p.tiles_h;
+      const int n0 = nt * p.BN;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      __nv_bfloat16* dst = p.y + ((((size_t)n * p.H + (ht * TH + pr)) * p.W + (wt * TW + pc)) * p.Cout + n0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+          if (p.bias) {
+            a = fmaf(p.bias[n0 + c0 + 2 * j], p.bias_mul, a);
+            b = fmaf(p.bias[n0 + c0 + 2 * j + 1], p.bias_mul, b);
+          }
+          if (p.act) { a = sg_lrelu(a); b = sg_lrelu(b); }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+          packed[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+        d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+static int pick_bn(int Cout) {
+  if (Cout % 128 == 0) return 128;
+  if (Cout <= 128 && Cout % 16 == 0) return Cout;
+  return 0;
+}
+
+}  // namespace tc
+
+SG_EXPORT int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout) {
+  if (N < 1 || H % tc::TH != 0 || W % tc::TW != 0) return 0;
+  if (Cin % tc::BK != 0) return 0;
+  if (tc::pick_bn(Cout) == 0) return 0;
+  return 1;
+}
 
 SG_EXPORT int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float* bias, float bias_mul, int act, int N,
                             int H, int W, int Cin, int Cout, void* stream) {
-  sg_set_error("sg_conv3x3_tc: shape not supported");
-  return 1002;
+  using namespace tc;
+  SG_REQUIRE(sg_conv3x3_tc_supported(N, H, W, Cin, Cout), "sg_conv3x3_tc: shape not supported");
+  EncodeTiledFn enc = get_encode();
+  SG_REQUIRE(enc != nullptr, "sg_conv3x3_tc: cuTensorMapEncodeTiled unavailable");
+  const int BN = pick_bn(Cout);
+
+  CUtensorMap map_x, map_w;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)(TH + 2), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SG_REQUIRE(r == CUDA_SUCCESS, "sg_conv3x3_tc: cuTensorMapEncodeTiled(x) failed");
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)9 * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(Etc), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SG_REQUIRE(r == CUDA_SUCCESS, "sg_conv3x3_tc: cuTensorMapEncodeTiled(w) failed");
+  }
+
+  Params p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.BN = BN;
+  p.tiles_h = H / TH; p.tiles_w = W / TW; p.tiles_n = Cout / BN;
+  p.num_tiles = N * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.kchunks = Cin / BK;
+  p.stage_bytes = A_BYTES + 3 * BN * BK * 2;
+  int stages = (216 * 1024) / p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  SG_REQUIRE(stages >= 2, "sg_conv3x3_tc: not enough shared memory for two stages");
+  p.stages = stages;
+  int cols = 2 * BN;
+  int tc_cols = 32;
+  while (tc_cols < cols) tc_cols <<= 1;
+  p.tmem_cols = tc_cols;
+  p.bias = bias; p.bias_mul = bias_mul; p.act = act;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+
+  size_t smem = (size_t)stages * p.stage_bytes + sizeof(Barriers) + 1024;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  SG_REQUIRE(attr_err == cudaSuccess, "sg_conv3x3_tc: cannot raise the dynamic shared memory limit");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  conv3x3_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_x, map_w, p);
+  return sg_check_launch("sg_conv3x3_tc");
 }

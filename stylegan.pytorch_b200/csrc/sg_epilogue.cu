@@ -1,10 +1,12 @@
 // Synthesis-layer epilogue (reference CustomLayers.py:219-248: noise -> LeakyReLU -> InstanceNorm -> StyleMod)
 // as two forward passes and two backward passes over NHWC activations:
 //   fwd 1  z = lrelu(y + b[c] + nw[c]*noise[n,p]);  S[n,c] += (z, z^2)            (sg_epi_act_stats)
-//   fwd 2  out = a[n,c]*z + d[n,c]   with a = rstd*(1+s0), d = s1 - mean*a        (sg_epi_finalize + sg_affine_nc)
+//   fwd 2  out = (z - mean[n,c])*a[n,c] + s1[n,c]   with a = rstd*(1+s0)          (sg_epi_finalize + sg_affine_nc)
 //   bwd 1  A[n,c] = sum_p g,  B[n,c] = sum_p g*xhat                               (sg_epi_bwd_reduce)
-//   bwd 2  g_pre = (c1*g + c2*z + c3) * lrelu'(z)                                 (sg_epi_bwd_finalize + _apply)
-// Per-(n,c) sums are accumulated in fp64 (block partials in fp32) so the one-pass variance is safe.
+//   bwd 2  g_pre = (c1*g + k*(z-mean) + c0) * lrelu'(z)                           (sg_epi_bwd_finalize + _apply)
+// Numerics: the statistics are sums of (z - K) with the pivot K[n,c] = z at the image's first pixel, so the one-pass
+// variance does not cancel even when mean^2 >> var (the 4x4 constant-input layer: z = 2 + small noise); block
+// partials are fp32, cross-block accumulation fp64.  All affine forms are written around (z - mean) for the same reason.
 #include "sg_common.cuh"
 #include "../../include/sgb200.h"
 
@@ -28,10 +30,16 @@ __global__ void epi_reduce_kernel(const T* __restrict__ in0, const T* __restrict
   const size_t base = (size_t)n * HW;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s0 = 0.f, s1 = 0.f;
-    float b = 0.f, nw = 0.f, mean = 0.f, rstd = 0.f;
+    float b = 0.f, nw = 0.f, mean = 0.f, rstd = 0.f, pivot = 0.f;
     if (MODE == 0) {
       b = bias ? bias[c] * bias_mul : 0.f;
       nw = (noise && noise_w) ? noise_w[c] : 0.f;
+      // pivot = z at pixel 0 of this image (identical in every CTA of the image)
+      float v0 = sg_to_f(in0[base * C + c]) + b;
+      if (noise) v0 = fmaf(nw, noise[base], v0);
+      if (act) v0 = sg_lrelu(v0);
+      pivot = sg_to_f(sg_from_f<T>(v0));
+      if (blockIdx.x == 0 && threadIdx.y == 0) sums[((size_t)n * C + c) * 3 + 2] = (double)pivot;
     } else {
       mean = mr[((size_t)n * C + c) * 2 + 0];
       rstd = mr[((size_t)n * C + c) * 2 + 1];
@@ -44,7 +52,7 @@ __global__ void epi_reduce_kernel(const T* __restrict__ in0, const T* __restrict
         if (act) v = sg_lrelu(v);
         T zt = sg_from_f<T>(v);
         zout[idx] = zt;
-        float zr = sg_to_f(zt);
+        float zr = sg_to_f(zt) - pivot;
         s0 += zr;
         s1 = fmaf(zr, zr, s1);
       } else {
@@ -64,7 +72,7 @@ __global__ void epi_reduce_kernel(const T* __restrict__ in0, const T* __restrict
     float s = 0.f;
 #pragma unroll
     for (int r = 0; r < EPI_ROWS; ++r) s += sm[(j * EPI_ROWS + r) * C + c];
-    atomicAdd(&sums[((size_t)n * C + c) * 2 + j], (double)s);
+    atomicAdd(&sums[((size_t)n * C + c) * 3 + j], (double)s);
   }
 }
 
@@ -74,21 +82,21 @@ __global__ void epi_finalize_kernel(const double* __restrict__ sums, const float
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   int n = i / C, c = i % C;
-  double m = sums[(size_t)i * 2] / HW;
-  double var = sums[(size_t)i * 2 + 1] / HW - m * m;
+  double m = sums[(size_t)i * 3] / HW;                       // mean of (z - pivot)
+  double var = sums[(size_t)i * 3 + 1] / HW - m * m;
   if (var < 0.0) var = 0.0;
   float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  float mean = (float)m;
+  float mean = (float)(m + sums[(size_t)i * 3 + 2]);
   mr[(size_t)i * 2] = mean;
   mr[(size_t)i * 2 + 1] = rstd;
   float s0 = style ? style[(size_t)n * 2 * C + c] : 0.f;
   float s1 = style ? style[(size_t)n * 2 * C + C + c] : 0.f;
-  float a = rstd * (1.f + s0);
-  ab[(size_t)i * 2] = a;
-  ab[(size_t)i * 2 + 1] = s1 - mean * a;
+  ab[(size_t)i * 3] = mean;
+  ab[(size_t)i * 3 + 1] = rstd * (1.f + s0);
+  ab[(size_t)i * 3 + 2] = s1;
 }
 
-// out[n,p,c] = ab[n,c,0]*z + ab[n,c,1]
+// out[n,p,c] = (z - mab[n,c,0]) * mab[n,c,1] + mab[n,c,2]
 template <class T>
 __global__ void affine_nc_kernel(const T* __restrict__ z, const float* __restrict__ ab, T* __restrict__ out, int N,
                                  int HW, int C) {
@@ -102,9 +110,9 @@ __global__ void affine_nc_kernel(const T* __restrict__ z, const float* __restric
     int n = (int)(p / HW);
     V v, o;
     v.load(z + (size_t)p * C + cv * V::N);
-    const float* q = ab + ((size_t)n * C + cv * V::N) * 2;
+    const float* q = ab + ((size_t)n * C + cv * V::N) * 3;
 #pragma unroll
-    for (int k = 0; k < V::N; ++k) o.set(k, fmaf(q[2 * k], v.get(k), q[2 * k + 1]));
+    for (int k = 0; k < V::N; ++k) o.set(k, fmaf(v.get(k) - q[3 * k], q[3 * k + 1], q[3 * k + 2]));
     o.store(out + (size_t)p * C + cv * V::N);
   }
 }
@@ -116,19 +124,19 @@ __global__ void affine_nc_scalar_kernel(const T* __restrict__ z, const float* __
        i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     int n = (int)(i / ((long long)HW * C));
-    const float* q = ab + ((size_t)n * C + c) * 2;
-    out[i] = sg_from_f<T>(fmaf(q[0], sg_to_f(z[i]), q[1]));
+    const float* q = ab + ((size_t)n * C + c) * 3;
+    out[i] = sg_from_f<T>(fmaf(sg_to_f(z[i]) - q[0], q[1], q[2]));
   }
 }
 
-// per-(n,c): style gradients and the coefficients of  g_z = c1*g + c2*z + c3
+// per-(n,c): style gradients and the coefficients of  g_z = c1*g + k*(z - mean) + c0
 __global__ void epi_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ mr,
                                         const float* __restrict__ style, float* __restrict__ gstyle,
                                         float* __restrict__ coef, int N, int C, int HW) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   int n = i / C, c = i % C;
-  float A = (float)sums[(size_t)i * 2], B = (float)sums[(size_t)i * 2 + 1];
+  float A = (float)sums[(size_t)i * 3], B = (float)sums[(size_t)i * 3 + 1];
   float mean = mr[(size_t)i * 2], rstd = mr[(size_t)i * 2 + 1];
   float s0 = style ? style[(size_t)n * 2 * C + c] : 0.f;
   if (gstyle) {
@@ -137,11 +145,10 @@ __global__ void epi_bwd_finalize_kernel(const double* __restrict__ sums, const f
   }
   float inv = 1.f / (float)HW;
   float c1 = rstd * (1.f + s0);
-  float c2 = -c1 * rstd * B * inv;
-  float c3 = c1 * (mean * rstd * B * inv - A * inv);
-  coef[(size_t)i * 3] = c1;
-  coef[(size_t)i * 3 + 1] = c2;
-  coef[(size_t)i * 3 + 2] = c3;
+  coef[(size_t)i * 4] = c1;
+  coef[(size_t)i * 4 + 1] = -c1 * rstd * B * inv;   // k
+  coef[(size_t)i * 4 + 2] = mean;
+  coef[(size_t)i * 4 + 3] = -c1 * A * inv;          // c0
 }
 
 template <class T>
@@ -152,9 +159,9 @@ __global__ void epi_bwd_apply_kernel(const T* __restrict__ g, const T* __restric
        i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     int n = (int)(i / ((long long)HW * C));
-    const float* q = coef + ((size_t)n * C + c) * 3;
+    const float* q = coef + ((size_t)n * C + c) * 4;
     float zv = sg_to_f(z[i]);
-    float gz = fmaf(q[0], sg_to_f(g[i]), fmaf(q[1], zv, q[2]));
+    float gz = fmaf(q[0], sg_to_f(g[i]), fmaf(q[1], zv - q[2], q[3]));
     gy[i] = sg_from_f<T>((!act || zv > 0.f) ? gz : SG_LRELU_SLOPE * gz);
   }
 }
@@ -181,7 +188,7 @@ int launch_reduce(const void* in0, const void* in1, void* zout, const float* bia
 
 }  // namespace
 
-// sums must be zeroed by the caller (N*C*2 doubles).
+// sums must be zeroed by the caller (N*C*3 doubles: sum, sum of squares, pivot).
 SG_EXPORT int sg_epi_act_stats(const void* y, const float* bias, float bias_mul, const float* noise,
                                const float* noise_w, int act, void* z, double* sums, int dtype, int N, int HW,
                                int C, void* stream) {

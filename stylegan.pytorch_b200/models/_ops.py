@@ -59,37 +59,42 @@ def _coef_dev(kind, k, direction, device):
     return c
 
 
-def prepped_weight(W, kind, direction, dtype, scale):
-    """Effective weights E[npt][A][B] in `dtype`.  Cached for nn.Parameters only, keyed on (storage, version,
+def cached_weight(W, sub, build):
+    """Derived (packed / scaled / bf16) copy of a weight, cached for nn.Parameters only, keyed on (storage, version,
     weights epoch): the fused optimizer writes parameters through raw pointers and bumps the epoch instead of the
     tensor version.  Code that edits `param.data` behind autograd's back must call clear_weight_cache()."""
-    Wd = W.detach()
-    co, ci, k, _ = W.shape
-    cacheable = isinstance(W, torch.nn.Parameter)
-    sub = (kind, direction, dtype, float(scale))
-    if cacheable:
-        key = (Wd.data_ptr(), W._version, _epoch[0], tuple(W.shape))
-        hit = _prep_cache.get(id(W))
-        if hit is not None and hit[0] == key:
-            E = hit[1].get(sub)
-            if E is not None:
-                return E
-        else:
-            if len(_prep_cache) > 2048:
-                _prep_cache.clear()
-            hit = (key, {})
-            _prep_cache[id(W)] = hit
-    t = _geom.tables(kind, k, direction)
-    npt = t["nphase"] * t["ntaps"]
-    a, b = (co, ci) if t["transpose"] else (ci, co)
-    E = torch.empty((npt, a, b), dtype=dtype, device=W.device)
-    coef = _coef_dev(kind, k, direction, W.device)
-    lib.sg_wprep_fwd(ptr(_c(Wd)), ptr(E), code(dtype), co, ci, k * k, npt, ptr(coef), float(scale), t["transpose"],
-                     stream())
-    count_launch()
-    if cacheable:
-        hit[1][sub] = E
+    if not isinstance(W, torch.nn.Parameter):
+        return build()
+    key = (W.data_ptr(), W._version, _epoch[0], tuple(W.shape))
+    hit = _prep_cache.get(id(W))
+    if hit is not None and hit[0] == key:
+        E = hit[1].get(sub)
+        if E is not None:
+            return E
+    else:
+        if len(_prep_cache) > 2048:
+            _prep_cache.clear()
+        hit = (key, {})
+        _prep_cache[id(W)] = hit
+    E = build()
+    hit[1][sub] = E
     return E
+
+
+def prepped_weight(W, kind, direction, dtype, scale):
+    """Effective weights E[npt][A][B] of the tap-table convolution in `dtype`."""
+    def build():
+        co, ci, k, _ = W.shape
+        t = _geom.tables(kind, k, direction)
+        npt = t["nphase"] * t["ntaps"]
+        a, b = (co, ci) if t["transpose"] else (ci, co)
+        E = torch.empty((npt, a, b), dtype=dtype, device=W.device)
+        coef = _coef_dev(kind, k, direction, W.device)
+        lib.sg_wprep_fwd(ptr(_c(W.detach())), ptr(E), code(dtype), co, ci, k * k, npt, ptr(coef), float(scale),
+                         t["transpose"], stream())
+        count_launch()
+        return E
+    return cached_weight(W, (kind, direction, dtype, float(scale)), build)
 
 
 _epoch = [0]
@@ -666,11 +671,11 @@ class Epilogue(Function):
         if style is not None:
             style = _c(style)
         z = torch.empty_like(y)
-        sums = torch.zeros((N, C, 2), dtype=torch.float64, device=dev)
+        sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
         lib.sg_epi_act_stats(ptr(y), ptr(bias), float(bias_mul), ptr(noise), ptr(noise_w if noise is not None else None),
                              int(act), ptr(z), ptr(sums), code(y.dtype), N, HW, C, stream())
         mr = torch.empty((N, C, 2), dtype=torch.float32, device=dev)
-        ab = torch.empty((N, C, 2), dtype=torch.float32, device=dev)
+        ab = torch.empty((N, C, 3), dtype=torch.float32, device=dev)
         lib.sg_epi_finalize(ptr(sums), ptr(style), ptr(mr), ptr(ab), N, C, HW, float(eps), stream())
         out = torch.empty_like(y)
         lib.sg_affine_nc(ptr(z), ptr(ab), ptr(out), code(y.dtype), N, HW, C, stream())
@@ -688,10 +693,10 @@ class Epilogue(Function):
         N, H, W, C = z.shape
         HW = H * W
         dev = z.device
-        sums = torch.zeros((N, C, 2), dtype=torch.float64, device=dev)
+        sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
         lib.sg_epi_bwd_reduce(ptr(g), ptr(z), ptr(mr), ptr(sums), code(z.dtype), N, HW, C, stream())
         gstyle = torch.empty((N, 2 * C), dtype=torch.float32, device=dev) if style is not None else None
-        coef = torch.empty((N, C, 3), dtype=torch.float32, device=dev)
+        coef = torch.empty((N, C, 4), dtype=torch.float32, device=dev)
         lib.sg_epi_bwd_finalize(ptr(sums), ptr(mr), ptr(style), ptr(gstyle), ptr(coef), N, C, HW, stream())
         gy = torch.empty_like(z)
         lib.sg_epi_bwd_apply(ptr(g), ptr(z), ptr(coef), int(act), ptr(gy), code(z.dtype), N, HW, C, stream())
@@ -871,7 +876,8 @@ class AffineNC(Function):
         N, C = x.shape[0], x.shape[-1]
         HW = x.numel() // (N * C)
         out = torch.empty_like(x)
-        lib.sg_affine_nc(ptr(x), ptr(ab), ptr(out), code(x.dtype), N, HW, C, stream())
+        mab = torch.cat([torch.zeros_like(ab[..., :1]), ab], dim=-1).contiguous()      # (mean=0, a, b)
+        lib.sg_affine_nc(ptr(x), ptr(mab), ptr(out), code(x.dtype), N, HW, C, stream())
         count_launch()
         ctx.save_for_backward(x, ab)
         return out
@@ -886,12 +892,13 @@ class AffineNC(Function):
         dev = x.device
         gx = gab = None
         if ctx.needs_input_grad[0]:
-            a0 = torch.stack([ab[..., 0], torch.zeros_like(ab[..., 0])], dim=-1).contiguous()
+            z0 = torch.zeros_like(ab[..., 0])
+            a0 = torch.stack([z0, ab[..., 0], z0], dim=-1).contiguous()
             gx = torch.empty_like(x)
             lib.sg_affine_nc(ptr(g), ptr(a0), ptr(gx), code(x.dtype), N, HW, C, stream())
             count_launch()
         if ctx.needs_input_grad[1]:
-            sums = torch.zeros((N, C, 2), dtype=torch.float64, device=dev)
+            sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
             mr = torch.zeros((N, C, 2), dtype=torch.float32, device=dev)
             mr[..., 1] = 1.0
             lib.sg_epi_bwd_reduce(ptr(g), ptr(x), ptr(mr), ptr(sums), code(x.dtype), N, HW, C, stream())

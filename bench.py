@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the StyleGAN G+D training step (BASELINE.json metric: images/sec @256x256, batch 32 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--res 256] [--batch 32] [--precision bf16]
+
+One "step" = StyleGAN.optimize_discriminator + StyleGAN.optimize_generator (logistic loss with R1, EMA, style mixing,
+truncation; reference models/GAN.py:591-659) on synthetic NCHW batches with random-init weights.  For N > 1 launch under
+torch.distributed.run (one rank per GPU, NCCL); per-GPU work is fixed (weak scaling), `value` is the whole-job
+images/sec from the max-over-ranks device time.  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the CPU oracle port of the reference path (oracle/stylegan_oracle.py; the reference itself
+is a Python package that does not exist on the GPU box) on the host cores with a bounded batch per step."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "stylegan.pytorch_b200"))
+sys.dont_write_bytecode = True
+
+F_STEP_GFLOP = {128: 656.7, 256: 822.8, 1024: 1162.0}     # BASELINE.md section 3 (reference formulation, per image)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_gan(res, precision, device, seed):
+    import torch
+    import models
+    from models.GAN import StyleGAN
+    models.set_precision(precision)
+    torch.manual_seed(seed)
+    g_args = dict(latent_size=512, mapping_layers=4, blur_filter=[1, 2, 1], truncation_psi=0.7, truncation_cutoff=8)
+    d_args = dict(use_wscale=True, blur_filter=[1, 2, 1])
+    opt = dict(learning_rate=0.003, beta_1=0, beta_2=0.99, eps=1e-8)           # config.py:79-92
+    sg = StyleGAN(structure="linear", resolution=res, num_channels=3, latent_size=512, g_args=g_args, d_args=d_args,
+                  g_opt_args=opt, d_opt_args=dict(opt), loss="logistic", use_ema=True, ema_decay=0.999, device=device)
+    sg.gen.train(); sg.dis.train(); sg.gen_shadow.train()
+    # the reference initialises noise weights to zero (CustomLayers.py:188); randomise so the noise path does work
+    with torch.no_grad():
+        for n, p in sg.gen.named_parameters():
+            if n.endswith("noise.weight"):
+                p.copy_(torch.randn_like(p))
+        sg.gen_shadow.load_state_dict(sg.gen.state_dict())
+    return sg
+
+
+def northstar_kernel_roofline(batch, res, ch, iters=20):
+    """The fused 3x3 synthesis conv (blocks[-1].conv1: ch->ch at res x res), timed alone with CUDA events."""
+    import torch
+    from models import _tc
+    from models._lib import lib, ptr, stream
+    if not lib.sg_conv3x3_tc_supported(batch, res, res, ch, ch):
+        return None
+    dev = "cuda"
+    x = torch.randn(batch, res, res, ch, device=dev).bfloat16()
+    W = torch.nn.Parameter(torch.randn(ch, ch, 3, 3, device=dev))
+    b = torch.randn(ch, device=dev)
+    y = torch.empty_like(x)
+    E = _tc.tc_weight(W, "fwd", 0.05)
+    st = stream()
+
+    def run():
+        lib.sg_conv3x3_tc(ptr(x), ptr(E), ptr(y), ptr(b), 1.0, 1, batch, res, res, ch, ch, st)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    # input+output (2 x 268 MB at the north-star shape) exceed the 126 MB L2, so successive launches do not hit in L2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * batch * res * res * ch * ch * 9
+    pk, how = peaks()
+    ach = flops / (ms * 1e-3) / 1e12
+    alg_bytes = 2.0 * batch * res * res * ch * 2 + 9 * ch * ch * 2
+    return {"bound": "tensor", "kernel": "conv3x3_tc_kernel %d->%d @%dx%d N=%d (fused bias+LeakyReLU)" % (ch, ch, res, res, batch),
+            "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4),
+            "peak_source": how + " (burst cuBLAS bf16; kernel timed alone)", "ms_per_launch": round(ms, 4),
+            "algorithmic_gflop_per_launch": round(flops / 1e9, 1),
+            "hbm_gbs_algorithmic": round(alg_bytes / (ms * 1e-3) / 1e9, 1), "traffic": None}
+
+
+def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):
+    """Times the oracle port of the reference's G+D step on the host cores.  -> (seconds/step list, threads)."""
+    import random
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stylegan_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0); random.seed(0)
+    arch = O.Arch(res)
+    gen = torch.Generator().manual_seed(0)
+    st = O.TrainState(arch, O.init_generator(arch, gen), O.init_discriminator(arch, gen))
+    depth = arch.depth - 1
+    times = []
+    for i in range(warmup + steps):
+        real = torch.randn(batch, 3, res, res)
+        z = torch.randn(batch, 512)
+        noises_d = [torch.randn(s) for s in O.noise_shapes(arch, batch, depth)]
+        noises_g = [torch.randn(s) for s in O.noise_shapes(arch, batch, depth)]
+        mix_d, mix_g = O.draw_mixing(arch, z.shape, depth), O.draw_mixing(arch, z.shape, depth)
+        t0 = time.perf_counter()
+        O.train_step(st, real, z, depth, 0.5, mix_d, mix_g, noises_d, noises_g)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    times, threads = cpu_oracle_step_time(args.res, batch, args.steps, args.warmup)
+    sec = sum(times) / len(times)
+    val = batch / sec
+    out = {"impl": "reference", "metric": "images/sec G+D step @%dx%d bs=%d/GPU" % (args.res, args.res, args.batch),
+           "value": round(val, 4),
+           "unit": "images/sec", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "G+D step (logistic+R1, EMA) %dx%d depth %d" % (args.res, args.res, O_depth(args.res)),
+                      "batch_per_step": batch, "device": "host CPU"},
+           "cpu_baseline": {"value": round(val, 4), "unit": "images/sec", "cores": threads, "kind": "port",
+                            "sample": "%d timed G+D steps at batch %d (the reference is Python and absent on the GPU "
+                                      "box; this is oracle/stylegan_oracle.py, pinned to it in the build container)"
+                                      % (args.steps, batch)},
+           "e2e": {"value": round(val, 4), "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def O_depth(res):
+    import math
+    return int(math.log2(res)) - 2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sgb200")
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    if not os.environ.get("SG_BENCH_QUICK"):
+        args.warmup = max(args.warmup, 3)
+    verbose = bool(os.environ.get("SG_BENCH_VERBOSE"))
+
+    from models import _lib
+    sg = make_gan(args.res, args.precision, device, seed=1234 + rank)
+    depth, alpha, B, R = O_depth(args.res), 0.5, args.batch, args.res
+    torch.manual_seed(99 + rank)
+    n_buf = 4
+    imgs_dev = [torch.randn(B, 3, R, R, device=device) for _ in range(n_buf)]
+    z_dev = [torch.randn(B, 512, device=device) for _ in range(n_buf)]
+    imgs_host = [torch.randn(B, 3, R, R).pin_memory() for _ in range(n_buf)]
+    z_host = [torch.randn(B, 512).pin_memory() for _ in range(n_buf)]
+
+    def step_resident(i):
+        t0 = time.perf_counter()
+        sg.optimize_discriminator(z_dev[i % n_buf], imgs_dev[i % n_buf], depth, alpha)
+        t1 = time.perf_counter()
+        sg.optimize_generator(z_dev[i % n_buf], imgs_dev[i % n_buf], depth, alpha)
+        if verbose and rank == 0:
+            print("step %d: D %.3fs G %.3fs  mem %.1f GB" % (i, t1 - t0, time.perf_counter() - t1,
+                                                         torch.cuda.max_memory_allocated() / 2 ** 30),
+                  file=sys.stderr, flush=True)
+
+    def step_e2e(i):
+        img = imgs_host[i % n_buf].to(device, non_blocking=True)
+        z = z_host[i % n_buf].to(device, non_blocking=True)
+        dl = sg.optimize_discriminator(z, img, depth, alpha)      # returns loss.item(): device->host read each step
+        gl = sg.optimize_generator(z, img, depth, alpha)
+        return dl, gl
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launches()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        pk, how = peaks()
+        value = world * B * args.steps / (ms * 1e-3)
+        e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        fstep = F_STEP_GFLOP.get(R)
+        out = {"metric": "images/sec G+D step @%dx%d bs=%d/GPU" % (R, R, B), "value": round(value, 2),
+               "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
+               "data": "synthetic",
+               "config": {"workload": "StyleGAN G+D step (optimize_discriminator + optimize_generator, logistic + R1, "
+                                      "EMA, style mixing, truncation) %dx%d depth %d alpha 0.5" % (R, R, depth),
+                          "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                          "l2": "per-step activations (GBs) exceed the 126 MB L2; no explicit flush"},
+               "e2e": {"value": round(e2e, 2), "unit": "images/sec", "ms_per_step": round(ms_e2e / args.steps, 3),
+                       "h2d_bytes_per_step": B * 3 * R * R * 4 + B * 512 * 4, "d2h_bytes_per_step": 8},
+               "gpu_launches": int(launches), "clocks": clocks}
+        if fstep:
+            out["step_tensor_fraction"] = {"algorithmic_gflop_per_image": fstep,
+                                           "achieved_tflops_per_gpu": round(value / world * fstep / 1e3, 1),
+                                           "frac_of_sustained_bf16_peak": round(value / world * fstep / 1e3 /
+                                                                                pk["bf16_tflops_sustained"], 4),
+                                           "peak_source": how}
+        ch = {128: 128, 256: 64, 512: 32, 1024: 16}.get(R, 64)
+        try:
+            out["roofline"] = northstar_kernel_roofline(B, R, ch) if args.precision == "bf16" else None
+        except Exception as e:                              # the roofline probe must never lose the headline number
+            out["roofline"] = {"error": str(e)[:200]}
+        if world == 1 and not args.no_cpu_baseline:
+            t, threads = cpu_oracle_step_time(R, args.ref_batch, 1, 0)
+            out["cpu_baseline"] = {"value": round(args.ref_batch / t[0], 4), "unit": "images/sec", "cores": threads,
+                                   "kind": "port", "sample": "1 G+D step at %dx%d, batch %d, oracle port on host CPU"
+                                                              % (R, R, args.ref_batch)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

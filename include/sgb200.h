@@ -66,6 +66,13 @@ int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout);
 int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float* bias, float bias_mul, int act, int N, int H,
                   int W, int Cin, int Cout, void* stream);
 
+/* tcgen05/TMA weight gradient of the same convolution: part [S][9][Cout][Cin] float32 partial sums over S pixel splits
+ * (S = sg_wgrad3x3_tc_splits); reduce + scale + OIHW layout with sg_wprep_bwd(transpose=1).  x [N,H,W,Cin], dy
+ * [N,H,W,Cout] bf16.  Adjoint of models/CustomLayers.py:170-171 wrt the weight; also used by the R1 double backward. */
+int sg_wgrad3x3_tc_supported(int N, int H, int W, int Cin, int Cout);
+int sg_wgrad3x3_tc_splits(int N, int H, int W, int Cin, int Cout);
+int sg_wgrad3x3_tc(const void* x, const void* dy, float* part, int N, int H, int W, int Cin, int Cout, void* stream);
+
 /* ---- bandwidth-bound feature-map kernels ------------------------------------------------------------------------ */
 /* BlurLayer.forward, CustomLayers.py:266-276 (+ the `x + bias` of :178-179 when bias != NULL). Self-adjoint. */
 int sg_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W, int C,

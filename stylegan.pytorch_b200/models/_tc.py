@@ -52,5 +52,27 @@ def try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
     return True
 
 
+def _eye9(device):
+    c = _coef.get(("eye", device))
+    if c is None:
+        c = torch.eye(9, dtype=torch.float32, device=device)
+        _coef[("eye", device)] = c
+    return c
+
+
 def try_wgrad(xl, dyl, kind, scale, dW):
-    return False
+    """dW[co][ci][kh][kw] = scale * sum_p dy[p][co] x[p + (kh-1,kw-1)][ci] on the tensor cores."""
+    if not _ops._state["use_tc"] or xl.dtype != torch.bfloat16 or kind != "same":
+        return False
+    co, ci, k, _ = dW.shape
+    if k != 3:
+        return False
+    N, H, Wd, _ = xl.shape
+    if not lib.sg_wgrad3x3_tc_supported(N, H, Wd, ci, co):
+        return False
+    S = lib.sg_wgrad3x3_tc_splits(N, H, Wd, ci, co)
+    part = torch.empty((S, 9, co, ci), dtype=torch.float32, device=xl.device)
+    lib.sg_wgrad3x3_tc(ptr(xl), ptr(dyl), ptr(part), N, H, Wd, ci, co, stream())
+    lib.sg_wprep_bwd(ptr(part), S, ptr(dW), co, ci, 9, 9, ptr(_eye9(xl.device)), float(scale), 1, 0, stream())
+    count_launch(2)
+    return True

@@ -60,3 +60,24 @@ def test_unsupported_shapes_fall_back_to_generic_kernel():
     assert lib.sg_conv3x3_tc_supported(2, 4, 4, 64, 64) == 0      # below the 8x16 tile
     assert lib.sg_conv3x3_tc_supported(2, 16, 16, 32, 64) == 0    # Cin not a multiple of 64
     assert lib.sg_conv3x3_tc_supported(2, 16, 16, 64, 513) == 0
+
+
+@pytest.mark.parametrize("N,H,W,ci,co", [(2, 16, 16, 64, 64), (1, 8, 32, 64, 128), (3, 32, 32, 128, 64),
+                                          (2, 16, 16, 512, 512), (2, 64, 64, 64, 64), (4, 32, 16, 256, 128),
+                                          (5, 8, 16, 128, 128)])
+def test_wgrad3x3_tc_matches_oracle(N, H, W, ci, co):
+    from models import _ops, _tc
+    from models._lib import lib
+    torch.manual_seed(1)
+    assert lib.sg_wgrad3x3_tc_supported(N, H, W, ci, co) == 1
+    x = torch.randn(N, ci, H, W).bfloat16().float()
+    dy = torch.randn(N, co, H, W).bfloat16().float()
+    scale = 0.37
+    Wr = torch.zeros(co, ci, 3, 3, requires_grad=True)
+    (ref,) = torch.autograd.grad(F.conv2d(x, Wr * scale, padding=1), Wr, dy)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+    dyd = dy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+    dW = torch.empty(co, ci, 3, 3, device=DEV)
+    assert _tc.try_wgrad(xd, dyd, "same", scale, dW)
+    torch.cuda.synchronize()
+    assert rel(dW, ref) < 1e-4           # exact bf16 products, fp32 accumulation

@@ -80,6 +80,11 @@ int sg_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtyp
 /* y = x + bias[c]*bias_mul + noise_w[c]*noise[n,p]: stand-alone NoiseLayer (CustomLayers.py:191-200) / bias add (:178). */
 int sg_bias_noise(const void* x, const float* bias, float bias_mul, const float* noise, const float* noise_w, int act,
                   void* y, int dtype, long long P, int C, void* stream);
+/* NHWC nearest x2 (Upscale2d, CustomLayers.py:27-36) and 2x2 box pooling with fused bias + LeakyReLU (Downscale2d,
+ * CustomLayers.py:48-64, + :178-179): the pre/post passes of the tensor-core up/down convolutions. */
+int sg_up2_nhwc(const void* x, void* y, float scale, int dtype, int N, int H, int W, int C, void* stream);
+int sg_pool2_nhwc(const void* x, void* y, const float* bias, float bias_mul, int act, float scale, int dtype, int N,
+                  int Ho, int Wo, int C, void* stream);
 /* out = a*x + b*y (y may be NULL): fade-in lerps GAN.py:202,427,586; scaling. */
 int sg_axpby(const void* x, const void* y, void* out, float a, float b, long long n, int dtype, void* stream);
 /* LeakyReLU(0.2) backward from the activation output (GAN.py:68,151,347). */

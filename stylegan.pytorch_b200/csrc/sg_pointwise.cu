@@ -374,6 +374,65 @@ __global__ void dlatents_bwd_kernel(const float* __restrict__ g, float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// NHWC 2x nearest up-sampling (times scale) and 2x2 box-sum pooling (times scale, + optional bias and LeakyReLU):
+// an adjoint pair.  Used to put the reference's unfused up/down convolutions (CustomLayers.py:153-154, 166-176)
+// on the tensor-core 3x3 kernel: nearest-up -> conv3x3, conv3x3 -> 2x2 box.
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void up2_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, float scale, int N, int H, int W, int C) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int ox = (int)(p % Wo);
+    long long r = p / Wo;
+    int oy = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    V v, o;
+    v.load(x + (((size_t)n * H + (oy >> 1)) * W + (ox >> 1)) * C + cv * V::N);
+    if (scale == 1.f) o = v;
+    else {
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) o.set(k, v.get(k) * scale);
+    }
+    o.store(y + (size_t)p * C + cv * V::N);
+  }
+}
+
+template <class T>
+__global__ void pool2_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ bias,
+                                  float bias_mul, int act, float scale, int N, int Ho, int Wo, int C) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const int H = 2 * Ho, W = 2 * Wo;
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int ox = (int)(p % Wo);
+    long long r = p / Wo;
+    int oy = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    const T* src = x + (((size_t)n * H + 2 * oy) * W + 2 * ox) * C + cv * V::N;
+    V a, b, c, d, o;
+    a.load(src); b.load(src + C); c.load(src + (size_t)W * C); d.load(src + (size_t)W * C + C);
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) {
+      float v = (a.get(k) + b.get(k) + c.get(k) + d.get(k)) * scale;
+      if (bias) v = fmaf(bias[cv * V::N + k], bias_mul, v);
+      if (act) v = sg_lrelu(v);
+      o.set(k, v);
+    }
+    o.store(y + (size_t)p * C + cv * V::N);
+  }
+}
+
 // y = x + bias[c]*bias_mul + noise_w[c]*noise[n,p]   (stand-alone NoiseLayer / bias add; CustomLayers.py:191-200,178)
 template <class T>
 __global__ void bias_noise_kernel(const T* __restrict__ x, const float* __restrict__ bias, float bias_mul,
@@ -557,4 +616,25 @@ SG_EXPORT int sg_dlatents_bwd(const float* g, float* gw1, float* gw2, int B, int
   long long total = (long long)B * D;
   dlatents_bwd_kernel<<<sg_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(g, gw1, gw2, B, L, D, mix_cutoff, psi, trunc_cutoff, has_trunc);
   return sg_check_launch("sg_dlatents_bwd");
+}
+
+SG_EXPORT int sg_up2_nhwc(const void* x, void* y, float scale, int dtype, int N, int H, int W, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    SG_REQUIRE(C % SgVec<T>::N == 0, "sg_up2_nhwc: C must be a multiple of the 16-byte vector width");
+    long long total = (long long)N * 4 * H * W * (C / SgVec<T>::N);
+    up2_nhwc_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)x, (T*)y, scale, N, H, W, C);
+  });
+  return sg_check_launch("sg_up2_nhwc");
+}
+
+SG_EXPORT int sg_pool2_nhwc(const void* x, void* y, const float* bias, float bias_mul, int act, float scale,
+                            int dtype, int N, int Ho, int Wo, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    SG_REQUIRE(C % SgVec<T>::N == 0, "sg_pool2_nhwc: C must be a multiple of the 16-byte vector width");
+    long long total = (long long)N * Ho * Wo * (C / SgVec<T>::N);
+    pool2_nhwc_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)x, (T*)y, bias, bias_mul, act, scale, N, Ho, Wo, C);
+  });
+  return sg_check_launch("sg_pool2_nhwc");
 }

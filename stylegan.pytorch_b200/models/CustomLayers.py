@@ -182,9 +182,7 @@ class EqualizedConv2d(nn.Module):
         kind = self.kind_for(x.shape[1], x.shape[2])
         bias = self.bias if (with_bias and self.bias is not None) else None
         b_mul = self.b_mul if self.bias is not None else 1.0
-        if bias is None and not act:
-            return _ops.Conv.apply(x, self.weight, kind, "fwd", self.w_mul)
-        return _ops.ConvBiasAct.apply(x, self.weight, bias, kind, self.w_mul, b_mul, act)
+        return _ops.conv_layer(x, self.weight, bias, kind, self.w_mul, b_mul, act)
 
     def forward_nhwc(self, x):
         if self.downscale is not None:

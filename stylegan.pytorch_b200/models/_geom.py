@@ -16,7 +16,7 @@ import numpy as np
 
 from ._lib import SgConvGeom
 
-KINDS = ("same", "down", "up", "up_fused")
+KINDS = ("same", "same_flip", "down", "up", "up_fused")
 
 
 def _merge_1d(kind):
@@ -35,12 +35,15 @@ def tables(kind, k, direction):
     (channels swap: E is laid out [.., Cout, Cin] -> transpose=1)."""
     assert kind in KINDS and direction in ("fwd", "dgrad")
     KK = k * k
-    if kind == "same":
+    if kind in ("same", "same_flip"):
+        # 'same_flip' = stride-1 conv with the kernel rotated by 180 degrees (the fused up-conv after a nearest x2)
         taps = [(kh, kw) for kh in range(k) for kw in range(k)]
         sgn = 1 if direction == "fwd" else -1
         dy = [[sgn * (kh - k // 2) for kh, kw in taps]]
         dx = [[sgn * (kw - k // 2) for kh, kw in taps]]
         coef = np.eye(KK, dtype=np.float32)
+        if kind == "same_flip":
+            coef = coef[::-1].copy()
         return dict(in_stride=1, out_stride=1, nphase=1, ntaps=KK, dy=dy, dx=dx, coef=coef,
                     transpose=int(direction == "dgrad"))
     assert k == 3
@@ -87,7 +90,7 @@ def tables(kind, k, direction):
 
 def out_hw(kind, direction, H, W):
     up = kind in ("up", "up_fused")
-    if kind == "same":
+    if kind in ("same", "same_flip"):
         return H, W
     grow = (up and direction == "fwd") or (kind == "down" and direction == "dgrad")
     return (2 * H, 2 * W) if grow else (H // 2, W // 2)

@@ -905,3 +905,73 @@ class AffineNC(Function):
             count_launch()
             gab = torch.stack([sums[..., 1], sums[..., 0]], dim=-1).float()   # d/da = sum g*x, d/db = sum g
         return gx, gab
+
+
+class UpNHWC(Function):
+    """Nearest x2 up-sampling of an NHWC feature map, times scale (adjoint: PoolNHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        _require_cuda(x)
+        x = _c(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+        lib.sg_up2_nhwc(ptr(x), ptr(y), float(scale), code(x.dtype), N, H, W, C, stream())
+        count_launch()
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return PoolNHWC.apply(g, None, 1.0, False, ctx.scale), None
+
+
+class PoolNHWC(Function):
+    """y = [lrelu](scale * (2x2 box sum of x) + bias*bias_mul) on NHWC feature maps (adjoint: UpNHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, bias_mul, act, scale):
+        _require_cuda(x)
+        x = _c(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+        lib.sg_pool2_nhwc(ptr(x), ptr(y), ptr(bias), float(bias_mul), int(act), float(scale), code(x.dtype), N, H // 2,
+                          W // 2, C, stream())
+        count_launch()
+        ctx.save_for_backward(y if act else None)
+        ctx.cfg = (bias is not None, bias_mul, act, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        has_bias, bias_mul, act, scale = ctx.cfg
+        g = LreluBwd.apply(gy, y) if act else gy
+        gx = UpNHWC.apply(g, scale) if ctx.needs_input_grad[0] else None
+        gb = None
+        if has_bias and ctx.needs_input_grad[1]:
+            gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1)
+        return gx, gb, None, None, None
+
+
+def conv_layer(x, W, bias, kind, scale, bias_mul, act):
+    """One EqualizedConv2d evaluation on NHWC activations.  In bf16 mode the up/down-sampling convolutions run as
+    the reference's unfused formulation (nearest-up -> conv3x3, conv3x3 -> 2x2 box; CustomLayers.py:153-154,166-176)
+    so that all their FLOPs are on the tcgen05 3x3 kernels; otherwise as one tap-merged convolution."""
+    co, ci, k, _ = W.shape
+    if kind in ("up", "up_fused", "down") and x.dtype == torch.bfloat16 and _state["use_tc"] and k == 3:
+        from . import _tc
+        N, H, Wd, _ = x.shape
+        Hh, Wh = (2 * H, 2 * Wd) if kind != "down" else (H, Wd)
+        if _tc.conv_and_wgrad_supported(N, Hh, Wh, ci, co):
+            if kind == "down":
+                y = Conv.apply(x, W, "same", "fwd", scale)
+                return PoolNHWC.apply(y, bias, bias_mul, act, 0.25)
+            k2 = "same" if kind == "up" else "same_flip"
+            xu = UpNHWC.apply(x, 1.0)
+            if bias is None and not act:
+                return Conv.apply(xu, W, k2, "fwd", scale)
+            return ConvBiasAct.apply(xu, W, bias, k2, scale, bias_mul, act)
+    if bias is None and not act:
+        return Conv.apply(x, W, kind, "fwd", scale)
+    return ConvBiasAct.apply(x, W, bias, kind, scale, bias_mul, act)

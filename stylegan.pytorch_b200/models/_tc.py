@@ -11,33 +11,40 @@ from . import _ops
 _coef = {}
 
 
-def _tc_coef(direction, device):
-    """fwd: E[t][co][ci] = s*W[co][ci][t];  dgrad: E[t][ci][co] = s*W[co][ci][8-t] (180-degree rotated taps)."""
-    key = (direction, device)
+def _tc_coef(flipped, device):
+    key = (bool(flipped), device)
     c = _coef.get(key)
     if c is None:
         m = np.eye(9, dtype=np.float32)
-        if direction == "dgrad":
+        if flipped:
             m = m[::-1].copy()
         c = torch.from_numpy(m).to(device)
         _coef[key] = c
     return c
 
 
-def tc_weight(W, direction, scale):
+def tc_weight(W, direction, scale, kind="same"):
+    """fwd: E[t][co][ci] = s*W[co][ci][t];  dgrad: E[t][ci][co] = s*W[co][ci][8-t] (180-degree rotated taps);
+    kind 'same_flip' rotates once more."""
     def build():
         co, ci = W.shape[0], W.shape[1]
         rows, cols = (co, ci) if direction == "fwd" else (ci, co)
+        flipped = (direction == "dgrad") != (kind == "same_flip")
         E = torch.empty((9, rows, cols), dtype=torch.bfloat16, device=W.device)
-        lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 9, ptr(_tc_coef(direction, W.device)),
+        lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 9, ptr(_tc_coef(flipped, W.device)),
                          float(scale), 1 if direction == "fwd" else 0, stream())
         count_launch()
         return E
-    return _ops.cached_weight(W, ("tc3x3", direction, float(scale)), build)
+    return _ops.cached_weight(W, ("tc3x3", kind, direction, float(scale)), build)
+
+
+def conv_and_wgrad_supported(N, H, W, ci, co):
+    return bool(lib.sg_conv3x3_tc_supported(N, H, W, ci, co)) and bool(lib.sg_conv3x3_tc_supported(N, H, W, co, ci)) \
+        and bool(lib.sg_wgrad3x3_tc_supported(N, H, W, ci, co))
 
 
 def try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
-    if not _ops._state["use_tc"] or x.dtype != torch.bfloat16 or kind != "same":
+    if not _ops._state["use_tc"] or x.dtype != torch.bfloat16 or kind not in ("same", "same_flip"):
         return False
     co, ci, k, _ = W.shape
     if k != 3:
@@ -46,23 +53,15 @@ def try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
     cin, cout = (ci, co) if direction == "fwd" else (co, ci)
     if not lib.sg_conv3x3_tc_supported(N, H, Wd, cin, cout):
         return False
-    E = tc_weight(W, direction, scale)
+    E = tc_weight(W, direction, scale, kind)
     lib.sg_conv3x3_tc(ptr(x), ptr(E), ptr(y), ptr(bias), float(bias_mul), int(act), N, H, Wd, cin, cout, stream())
     count_launch()
     return True
 
 
-def _eye9(device):
-    c = _coef.get(("eye", device))
-    if c is None:
-        c = torch.eye(9, dtype=torch.float32, device=device)
-        _coef[("eye", device)] = c
-    return c
-
-
 def try_wgrad(xl, dyl, kind, scale, dW):
     """dW[co][ci][kh][kw] = scale * sum_p dy[p][co] x[p + (kh-1,kw-1)][ci] on the tensor cores."""
-    if not _ops._state["use_tc"] or xl.dtype != torch.bfloat16 or kind != "same":
+    if not _ops._state["use_tc"] or xl.dtype != torch.bfloat16 or kind not in ("same", "same_flip"):
         return False
     co, ci, k, _ = dW.shape
     if k != 3:
@@ -73,6 +72,7 @@ def try_wgrad(xl, dyl, kind, scale, dW):
     S = lib.sg_wgrad3x3_tc_splits(N, H, Wd, ci, co)
     part = torch.empty((S, 9, co, ci), dtype=torch.float32, device=xl.device)
     lib.sg_wgrad3x3_tc(ptr(xl), ptr(dyl), ptr(part), N, H, Wd, ci, co, stream())
-    lib.sg_wprep_bwd(ptr(part), S, ptr(dW), co, ci, 9, 9, ptr(_eye9(xl.device)), float(scale), 1, 0, stream())
+    lib.sg_wprep_bwd(ptr(part), S, ptr(dW), co, ci, 9, 9, ptr(_tc_coef(kind == "same_flip", xl.device)), float(scale),
+                     1, 0, stream())
     count_launch(2)
     return True

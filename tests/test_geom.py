@@ -20,6 +20,8 @@ def ref_forward(kind, x, W, scale):
     ws = W * scale
     if kind == "same":
         return F.conv2d(x, ws, padding=W.shape[-1] // 2)
+    if kind == "same_flip":
+        return F.conv2d(x, ws.flip(2, 3), padding=W.shape[-1] // 2)
     if kind == "down":
         return F.avg_pool2d(F.conv2d(x, ws, padding=1), 2)
     if kind == "up":
@@ -29,7 +31,7 @@ def ref_forward(kind, x, W, scale):
     return F.conv_transpose2d(x, wt, stride=2, padding=1)
 
 
-@pytest.mark.parametrize("kind,k", [("same", 3), ("same", 1), ("down", 3), ("up", 3), ("up_fused", 3)])
+@pytest.mark.parametrize("kind,k", [("same", 3), ("same", 1), ("same_flip", 3), ("down", 3), ("up", 3), ("up_fused", 3)])
 def test_forward_and_dgrad_tables(kind, k):
     torch.manual_seed(0)
     N, Ci, Co, H, W_ = 2, 5, 7, 8, 6
@@ -68,3 +70,14 @@ def test_geom_struct_fields():
     g = G.make_geom("down", 3, "fwd", 2, 64, 64, 8, 4)
     assert (g.Hq, g.Hout, g.in_stride, g.out_stride, g.nphase, g.ntaps) == (32, 32, 2, 1, 1, 16)
     assert [g.dy[0][i] for i in range(16)] == [u - 1 for u in range(4) for _ in range(4)]
+
+
+def test_up_fused_is_flipped_conv_after_nearest_up():
+    """The identity the bf16 tensor-core path relies on: conv_transpose2d of the box-summed kernel ==
+    nearest x2 followed by a stride-1 conv with the 180-degree rotated kernel."""
+    torch.manual_seed(2)
+    x = torch.randn(2, 5, 64, 64, dtype=torch.float64)
+    w = torch.randn(7, 5, 3, 3, dtype=torch.float64)
+    fused = ref_forward("up_fused", x, w, 1.0)
+    alt = F.conv2d(O.nearest_up2(x), w.flip(2, 3), padding=1)
+    assert torch.allclose(fused, alt, atol=1e-10)

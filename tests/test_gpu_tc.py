@@ -81,3 +81,30 @@ def test_wgrad3x3_tc_matches_oracle(N, H, W, ci, co):
     assert _tc.try_wgrad(xd, dyd, "same", scale, dW)
     torch.cuda.synchronize()
     assert rel(dW, ref) < 1e-4           # exact bf16 products, fp32 accumulation
+
+
+@pytest.mark.parametrize("kind,ci,co,hw", [("up", 128, 64, 16), ("up_fused", 128, 64, 64), ("down", 64, 128, 32),
+                                            ("down", 64, 128, 128)])
+def test_up_down_layers_on_tensor_cores(kind, ci, co, hw):
+    """bf16 up/down EqualizedConv2d layers (nearest-up -> tc conv, tc conv -> box pool) vs the oracle, fwd + grads."""
+    from models import _ops
+    import test_gpu_ops as T
+    torch.manual_seed(3)
+    N = 2
+    x = torch.randn(N, ci, hw, hw).bfloat16().float()
+    scale = O.he_scale(ci * 9, math.sqrt(2))
+    W = ((torch.randn(co, ci, 3, 3) * scale).bfloat16().float() / scale)
+    b = torch.randn(co)
+    xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = F.leaky_relu(T._ref_conv(kind, xr, Wr, scale) + br.view(1, -1, 1, 1), 0.2)
+    gy = torch.randn_like(y_ref)
+    ref = torch.autograd.grad(y_ref, [xr, Wr, br], gy)
+    _ops.clear_weight_cache()
+    launches0 = None
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16().requires_grad_(True)
+    Wd, bd = torch.nn.Parameter(W.to(DEV)), torch.nn.Parameter(b.to(DEV))
+    y = _ops.conv_layer(xd, Wd, bd, kind, scale, 1.0, True)
+    assert rel(y.float().permute(0, 3, 1, 2), y_ref) < 1e-2
+    got = torch.autograd.grad(y, [xd, Wd, bd], gy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16())
+    assert rel(got[0].float().permute(0, 3, 1, 2), ref[0]) < 6e-2
+    assert rel(got[1], ref[1]) < 6e-2 and rel(got[2], ref[2]) < 6e-2

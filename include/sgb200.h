@@ -108,7 +108,9 @@ int sg_rgb_out_dgrad(const float* g, const float* W, float coef, void* gx, int d
 /* AvgPool2d / nearest interpolate on NCHW float images: GAN.py:382, 575-586 */
 int sg_pool_nchw(const float* in, float* out, long long planes, int Ho, int Wo, int f, float scale, void* stream);
 int sg_upsample_nchw(const float* in, float* out, long long planes, int Hi, int Wi, int f, float scale, void* stream);
-int sg_plane_sum(const float* g, float* out, int N, int K, int HW, float scale, int accumulate, void* stream);
+/* ws: K*64 floats */
+int sg_plane_sum(const float* g, float* out, float* ws, int N, int K, int HW, float scale, int accumulate,
+                 void* stream);
 /* style mixing + truncation: GAN.py:281-293, CustomLayers.py:319-323 */
 int sg_dlatents(const float* w1, const float* w2, const float* avg, float* out, int B, int L, int D, int mix_cutoff,
                 float psi, int trunc_cutoff, void* stream);

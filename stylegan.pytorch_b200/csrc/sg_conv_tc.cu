@@ -28,6 +28,7 @@ struct __align__(8) Barriers {
   uint64_t empty[MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t wfull;
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -36,8 +37,9 @@ using namespace tcu;
 
 struct Params {
   int N, H, W, Cin, Cout, BN;
-  int tiles_h, tiles_w, tiles_n, num_tiles;
+  int tiles_h, tiles_w, tiles_n, num_spatial;
   int kchunks, stages, stage_bytes, tmem_cols;
+  int resident, w_bytes;      // resident: all 9*kchunks weight tiles of this CTA's N block stay in shared memory
   const float* bias;
   float bias_mul;
   int act;
@@ -49,12 +51,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint8_t* smem_w = smem + (size_t)p.stages * p.stage_bytes;          // resident weights (if any)
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_w + p.w_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a CTA keeps one N block for its whole life and walks the spatial tiles with stride gridDim.x / tiles_n
+  const int nt = blockIdx.x % p.tiles_n;
+  const int sp0 = blockIdx.x / p.tiles_n, sp_step = gridDim.x / p.tiles_n;
+  const int n0 = nt * p.BN;
+  __shared__ float s_bias[128];
+  for (int i = threadIdx.x; i < p.BN; i += blockDim.x) s_bias[i] = p.bias ? p.bias[n0 + i] * p.bias_mul : 0.f;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
+    mbar_init(&bars->wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&map_x);
     prefetch_tmap(&map_w);
@@ -74,24 +84,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.resident) {
+        mbar_expect_tx(&bars->wfull, (uint32_t)p.w_bytes);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int t = 0; t < 9; ++t)
+            tma_load_2d(smem_w + (size_t)(kc * 9 + t) * b_tap_bytes, &map_w, &bars->wfull, kc * BK, t * p.Cout + n0);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int nt = tile % p.tiles_n;
-        int r = tile / p.tiles_n;
+      for (int sp = sp0; sp < p.num_spatial; sp += sp_step) {
+        int r = sp;
         int wt = r % p.tiles_w; r /= p.tiles_w;
         int ht = r % p.tiles_h;
         int n = r / p.tiles_h;
-        const int h0 = ht * TH, w0 = wt * TW, n0 = nt * p.BN;
+        const int h0 = ht * TH, w0 = wt * TW;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int kw = 0; kw < 3; ++kw) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
             uint8_t* sB = sA + A_BYTES;
-            mbar_expect_tx(&bars->full[stage], (uint32_t)(A_BYTES + 3 * b_tap_bytes));
+            mbar_expect_tx(&bars->full[stage], (uint32_t)(p.resident ? A_BYTES : A_BYTES + 3 * b_tap_bytes));
             tma_load_4d(sA, &map_x, &bars->full[stage], kc * BK, w0 + kw - 1, h0 - 1, n);
-            for (int kh = 0; kh < 3; ++kh)
-              tma_load_2d(sB + kh * b_tap_bytes, &map_w, &bars->full[stage], kc * BK, (kh * 3 + kw) * p.Cout + n0);
+            if (!p.resident)
+              for (int kh = 0; kh < 3; ++kh)
+                tma_load_2d(sB + kh * b_tap_bytes, &map_w, &bars->full[stage], kc * BK, (kh * 3 + kw) * p.Cout + n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -99,38 +115,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+    // The whole warp walks the pipeline with warp-uniform state; one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = make_idesc_bf16(128, p.BN);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t sW = smem_u32(smem_w);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (p.resident) { mbar_wait(&bars->wfull, 0); tc_fence_after(); }
+    const uint32_t b_kh_stride = p.resident ? (uint32_t)(3 * b_tap_bytes) : (uint32_t)b_tap_bytes;
+    for (int sp = sp0; sp < p.num_spatial; sp += sp_step) {
+      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+      for (int it = 0; it < p.kchunks * 3; ++it) {
+        mbar_wait(&bars->full[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
-        uint32_t first = 1;
-        for (int it = 0; it < p.kchunks * 3; ++it) {
-          mbar_wait(&bars->full[stage], phase);
-          tc_fence_after();
-          const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sB = sA + A_BYTES;
+        const uint32_t sA = smem_base + (uint32_t)(stage * p.stage_bytes);
+        const int kw = it % 3, kc = it / 3;
+        // weights: streamed with the stage [kh][BN][64] or resident [kc][kh*3+kw][BN][64]
+        const uint32_t sB = p.resident ? (sW + (uint32_t)((kc * 9 + kw) * b_tap_bytes)) : (sA + A_BYTES);
+        const uint64_t a0 = make_desc_sw128(sA);
+        const uint64_t b0 = make_desc_sw128(sB);
+        const uint32_t bstep = b_kh_stride >> 4;
+        const bool leader = elect_one_sync();
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
+        for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              uint64_t ad = make_desc_sw128(sA + kh * (TW * 128) + k * 32);
-              uint64_t bd = make_desc_sw128(sB + kh * b_tap_bytes + k * 32);
-              umma_bf16(tmem_d, ad, bd, idesc, first ? 0u : 1u);
-              first = 0;
-            }
+          for (int k = 0; k < BK / 16; ++k) {
+            // descriptor start-address field is in 16-byte units: +kh*TW rows of 128 B, +k*32 B inside the atom
+            const uint64_t ad = a0 + (uint64_t)((kh * (TW * 128) + k * 32) >> 4);
+            const uint64_t bd = b0 + (uint64_t)(kh * bstep + ((k * 32) >> 4));
+            if (leader) umma_bf16(tmem_d, ad, bd, idesc, (it | kh | k) ? 1u : 0u);
           }
-          umma_commit(&bars->empty[stage]);          // frees the smem stage once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->tmem_full[acc]);           // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (leader) umma_commit(&bars->empty[stage]);          // frees the smem stage once these MMAs have read it
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
@@ -139,28 +165,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int pr = m / TW, pc = m % TW;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int nt = tile % p.tiles_n;
-      int r = tile / p.tiles_n;
+    for (int sp = sp0; sp < p.num_spatial; sp += sp_step) {
+      int r = sp;
       int wt = r % p.tiles_w; r /= p.tiles_w;
       int ht = r % p.tiles_h;
       int n = r / p.tiles_h;
-      const int n0 = nt * p.BN;
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       __nv_bfloat16* dst = p.y + ((((size_t)n * p.H + (ht * TH + pr)) * p.W + (wt * TW + pc)) * p.Cout + n0);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
+      auto emit16 = [&](const uint32_t (&v)[16], int c0) {
         uint32_t packed[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-          if (p.bias) {
-            a = fmaf(p.bias[n0 + c0 + 2 * j], p.bias_mul, a);
-            b = fmaf(p.bias[n0 + c0 + 2 * j + 1], p.bias_mul, b);
-          }
+          float a = __uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j];
+          float b = __uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1];
           if (p.act) { a = sg_lrelu(a); b = sg_lrelu(b); }
           __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
           packed[j] = *reinterpret_cast<uint32_t*>(&h2);
@@ -168,6 +187,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
         d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      };
+      for (int c0 = 0; c0 < p.BN; c0 += 64) {
+        // up to four 16-column TMEM loads in flight, one wait
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        const int nld = (p.BN - c0) >= 64 ? 4 : (p.BN - c0) / 16;
+        tmem_ld16_nowait(taddr + c0, v0);
+        if (nld > 1) tmem_ld16_nowait(taddr + c0 + 16, v1);
+        if (nld > 2) tmem_ld16_nowait(taddr + c0 + 32, v2);
+        if (nld > 3) tmem_ld16_nowait(taddr + c0 + 48, v3);
+        tmem_ld_wait();
+        emit16(v0, c0);
+        if (nld > 1) emit16(v1, c0 + 16);
+        if (nld > 2) emit16(v2, c0 + 32);
+        if (nld > 3) emit16(v3, c0 + 48);
       }
       tc_fence_before();
       __syncwarp();
@@ -186,7 +219,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-static int pick_bn(int Cout) {
+// Resident-weight mode: the 9*Cin*BN bf16 weights of one N block fit beside >= 3 activation stages.
+static bool resident_ok(int Cin, int Cout) { return Cin <= 128 && (Cout % 64 == 0 || (Cout < 64 && Cout % 16 == 0)); }
+static int pick_bn(int Cin, int Cout) {
+  if (resident_ok(Cin, Cout)) return Cout < 64 ? Cout : 64;
   if (Cout % 128 == 0) return 128;
   if (Cout <= 128 && Cout % 16 == 0) return Cout;
   return 0;
@@ -197,7 +233,7 @@ static int pick_bn(int Cout) {
 SG_EXPORT int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout) {
   if (N < 1 || H % tc::TH != 0 || W % tc::TW != 0) return 0;
   if (Cin % tc::BK != 0) return 0;
-  if (tc::pick_bn(Cout) == 0) return 0;
+  if (tc::pick_bn(Cin, Cout) == 0) return 0;
   return 1;
 }
 
@@ -207,7 +243,7 @@ SG_EXPORT int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float
   SG_REQUIRE(sg_conv3x3_tc_supported(N, H, W, Cin, Cout), "sg_conv3x3_tc: shape not supported");
   EncodeTiledFn enc = get_encode();
   SG_REQUIRE(enc != nullptr, "sg_conv3x3_tc: cuTensorMapEncodeTiled unavailable");
-  const int BN = pick_bn(Cout);
+  const int BN = pick_bn(Cin, Cout);
 
   CUtensorMap map_x, map_w;
   SG_REQUIRE(encode_nhwc(&map_x, x, N, H, W, Cin, TW, TH + 2), "sg_conv3x3_tc: cuTensorMapEncodeTiled(x) failed");
@@ -225,10 +261,12 @@ SG_EXPORT int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float
   Params p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.BN = BN;
   p.tiles_h = H / TH; p.tiles_w = W / TW; p.tiles_n = Cout / BN;
-  p.num_tiles = N * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.num_spatial = N * p.tiles_h * p.tiles_w;
   p.kchunks = Cin / BK;
-  p.stage_bytes = A_BYTES + 3 * BN * BK * 2;
-  int stages = (216 * 1024) / p.stage_bytes;
+  p.resident = resident_ok(Cin, Cout) ? 1 : 0;
+  p.w_bytes = p.resident ? 9 * p.kchunks * BN * BK * 2 : 0;
+  p.stage_bytes = p.resident ? A_BYTES : A_BYTES + 3 * BN * BK * 2;
+  int stages = (216 * 1024 - p.w_bytes) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   SG_REQUIRE(stages >= 2, "sg_conv3x3_tc: not enough shared memory for two stages");
   p.stages = stages;
@@ -239,17 +277,19 @@ SG_EXPORT int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float
   p.bias = bias; p.bias_mul = bias_mul; p.act = act;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
 
-  size_t smem = (size_t)stages * p.stage_bytes + sizeof(Barriers) + 1024;
+  size_t smem = (size_t)stages * p.stage_bytes + p.w_bytes + sizeof(Barriers) + 1024;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   });
   SG_REQUIRE(attr_err == cudaSuccess, "sg_conv3x3_tc: cannot raise the dynamic shared memory limit");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  int grid = (sms / p.tiles_n) * p.tiles_n;                  // every CTA keeps one N block
+  if (grid > p.num_spatial * p.tiles_n) grid = p.num_spatial * p.tiles_n;
+  SG_REQUIRE(grid >= p.tiles_n, "sg_conv3x3_tc: more N blocks than SMs");
   conv3x3_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_x, map_w, p);
   return sg_check_launch("sg_conv3x3_tc");
 }

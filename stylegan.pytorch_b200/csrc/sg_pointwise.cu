@@ -176,6 +176,58 @@ __global__ void channel_sum_kernel(const T* __restrict__ x, const float* __restr
   }
 }
 
+// Vectorised variant (C a multiple of the 16-byte vector width): a thread owns one 16-byte channel vector of a pixel
+// row and strides over pixels; per-thread partials for all rows live in registers; one smem reduction per block.
+template <class T>
+__global__ void __launch_bounds__(256) channel_sum_vec_kernel(const T* __restrict__ x, const float* __restrict__ wt,
+                                                              int J, int ones, long long P, int HW, int C,
+                                                              float* __restrict__ part, int pix_per_blk) {
+  using V = SgVec<T>;
+  extern __shared__ float sm[];                 // [rows][PR][C]
+  const int CV = C / V::N;
+  const int PR = blockDim.x / CV;               // pixel rows per iteration
+  const int cv = threadIdx.x % CV, pr = threadIdx.x / CV;
+  const int rows = J + (ones ? 1 : 0);
+  const long long p0 = (long long)blockIdx.x * pix_per_blk;
+  long long p1 = p0 + pix_per_blk;
+  if (p1 > P) p1 = P;
+  float acc[CS_ROWS][V::N];
+#pragma unroll
+  for (int j = 0; j < CS_ROWS; ++j)
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) acc[j][k] = 0.f;
+  if (pr < PR) {
+    for (long long p = p0 + pr; p < p1; p += PR) {
+      V v;
+      v.load(x + (size_t)p * C + cv * V::N);
+      long long n = p / HW;
+      int hw = (int)(p - n * HW);
+      float w[CS_ROWS];
+#pragma unroll
+      for (int j = 0; j < CS_ROWS; ++j) w[j] = (j < J) ? wt[((size_t)n * J + j) * HW + hw] : ((ones && j == J) ? 1.f : 0.f);
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) {
+        float f = v.get(k);
+#pragma unroll
+        for (int j = 0; j < CS_ROWS; ++j) acc[j][k] = fmaf(w[j], f, acc[j][k]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CS_ROWS; ++j)
+      if (j < rows) {
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) sm[((size_t)j * PR + pr) * C + cv * V::N + k] = acc[j][k];
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows * C; i += blockDim.x) {
+    int j = i / C, c = i % C;
+    float s = 0.f;
+    for (int r = 0; r < PR; ++r) s += sm[((size_t)j * PR + r) * C + c];
+    part[((size_t)blockIdx.x * rows + j) * C + c] = s;
+  }
+}
+
 __global__ void partial_reduce_kernel(const float* __restrict__ part, int nblk, int M, float* __restrict__ out,
                                       float scale, int accumulate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,6 +241,36 @@ __global__ void partial_reduce_kernel(const float* __restrict__ part, int nblk, 
 // from_rgb: img fp32 NCHW [N,K,H,W] -> y NHWC T [N,H,W,C]:  y = act(scale * sum_k W[c][k] img[k] + b[c]*bmul)
 // reference GAN.py:358,377 (1x1 EqualizedConv2d) + LeakyReLU.  K <= 4.
 // ---------------------------------------------------------------------------------------------------------
+// vectorised: one thread = one pixel x 16-byte channel vector
+template <class T>
+__global__ void rgb_in_vec_kernel(const float* __restrict__ img, const float* __restrict__ Wt,
+                                  const float* __restrict__ bias, float scale, float bias_mul, int act,
+                                  T* __restrict__ y, int N, int HW, int K, int C) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const long long total = (long long)N * HW * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    long long n = p / HW;
+    int hw = (int)(p - n * HW);
+    float px[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) px[k] = img[((size_t)n * K + k) * HW + hw];
+    V o;
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) {
+      int c = cv * V::N + e;
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = fmaf(Wt[c * K + k], px[k], s);
+      s = s * scale + (bias ? bias[c] * bias_mul : 0.f);
+      if (act) s = sg_lrelu(s);
+      o.set(e, s);
+    }
+    o.store(y + (size_t)p * C + cv * V::N);
+  }
+}
+
 template <class T>
 __global__ void rgb_in_kernel(const float* __restrict__ img, const float* __restrict__ Wt, const float* __restrict__ bias,
                               float scale, float bias_mul, int act, T* __restrict__ y, int N, int HW, int K, int C) {
@@ -325,16 +407,27 @@ __global__ void upsample_nchw_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-// out[k] = scale * sum_{n,hw} g[n,k,hw]  (to_rgb bias gradient); one block per k
-__global__ void plane_sum_kernel(const float* __restrict__ g, float* __restrict__ out, int N, int K, int HW,
-                                 float scale, int accumulate) {
+// out[k] = scale * sum_{n,hw} g[n,k,hw]  (to_rgb bias gradient); grid (K, PS_CHUNKS) partials, then a final pass
+constexpr int PS_CHUNKS = 64;
+__global__ void plane_sum_kernel(const float* __restrict__ g, float* __restrict__ part, int N, int K, int HW) {
   __shared__ float sm[32];
-  int k = blockIdx.x;
+  const int k = blockIdx.x, ch = blockIdx.y;
+  const long long total = (long long)N * HW;
   float s = 0.f;
-  for (int n = 0; n < N; ++n)
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += g[((size_t)n * K + k) * HW + i];
+  for (long long i = (long long)ch * blockDim.x + threadIdx.x; i < total; i += (long long)PS_CHUNKS * blockDim.x) {
+    long long n = i / HW;
+    s += g[((size_t)n * K + k) * HW + (i - n * HW)];
+  }
   s = sg_block_sum(s, sm);
-  if (threadIdx.x == 0) out[k] = (accumulate ? out[k] : 0.f) + s * scale;
+  if (threadIdx.x == 0) part[k * PS_CHUNKS + ch] = s;
+}
+__global__ void plane_sum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int K, float scale,
+                                       int accumulate) {
+  int k = threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int c = 0; c < PS_CHUNKS; ++c) s += part[k * PS_CHUNKS + c];
+  out[k] = (accumulate ? out[k] : 0.f) + s * scale;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -531,7 +624,14 @@ SG_EXPORT int sg_channel_sum(const void* x, int dtype, const float* wt, int J, i
   SG_REQUIRE(smem <= 48 * 1024, "sg_channel_sum: C too large");
   dim3 block(bx, R);
   SG_DISPATCH(dtype, {
-    channel_sum_kernel<T><<<nblk, block, smem, st>>>((const T*)x, wt, J, ones, P, HW, C, part_ws, pix_per_blk);
+    const int VN = SgVec<T>::N;
+    const int CV = C / VN;
+    if (C % VN == 0 && CV <= 256 && (size_t)rows * (256 / CV) * C * sizeof(float) <= 48 * 1024) {
+      size_t smv = (size_t)rows * (256 / CV) * C * sizeof(float);
+      channel_sum_vec_kernel<T><<<nblk, 256, smv, st>>>((const T*)x, wt, J, ones, P, HW, C, part_ws, pix_per_blk);
+    } else {
+      channel_sum_kernel<T><<<nblk, block, smem, st>>>((const T*)x, wt, J, ones, P, HW, C, part_ws, pix_per_blk);
+    }
   });
   int rc = sg_check_launch("sg_channel_sum");
   if (rc) return rc;
@@ -546,7 +646,10 @@ SG_EXPORT int sg_rgb_in(const float* img, const float* W, const float* bias, flo
   cudaStream_t st = (cudaStream_t)stream;
   long long total = (long long)N * HW * C;
   SG_DISPATCH(dtype, {
-    rgb_in_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);
+    if (C % SgVec<T>::N == 0)
+      rgb_in_vec_kernel<T><<<sg_grid_1d(total / SgVec<T>::N, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);
+    else
+      rgb_in_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);
   });
   return sg_check_launch("sg_rgb_in");
 }
@@ -598,9 +701,13 @@ SG_EXPORT int sg_upsample_nchw(const float* in, float* out, long long planes, in
   return sg_check_launch("sg_upsample_nchw");
 }
 
-SG_EXPORT int sg_plane_sum(const float* g, float* out, int N, int K, int HW, float scale, int accumulate,
+// ws: K*64 floats
+SG_EXPORT int sg_plane_sum(const float* g, float* out, float* ws, int N, int K, int HW, float scale, int accumulate,
                            void* stream) {
-  plane_sum_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(g, out, N, K, HW, scale, accumulate);
+  SG_REQUIRE(K >= 1 && K <= 32, "sg_plane_sum: K must be 1..32");
+  cudaStream_t st = (cudaStream_t)stream;
+  plane_sum_kernel<<<dim3(K, PS_CHUNKS), 256, 0, st>>>(g, ws, N, K, HW);
+  plane_sum_final_kernel<<<1, 32, 0, st>>>(ws, out, K, scale, accumulate);
   return sg_check_launch("sg_plane_sum");
 }
 

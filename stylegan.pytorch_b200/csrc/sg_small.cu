@@ -10,52 +10,90 @@ namespace {
 // one warp per output feature o, 8 batch rows at a time.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LIN_BB = 8;
-__global__ void linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W,
-                                  const float* __restrict__ bias, float scale, float bias_mul, int act,
-                                  float* __restrict__ y, int B, int I, int O) {
-  const int lane = threadIdx.x & 31;
-  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (o >= O) return;
-  const float* w = W + (size_t)o * I;
-  for (int b0 = 0; b0 < B; b0 += LIN_BB) {
-    float acc[LIN_BB];
+constexpr int LF_OB = 8;      // outputs per block (one warp each)
+constexpr int LF_IC = 256;    // input chunk staged in shared memory
+constexpr int LF_BMAX = 32;   // batch rows per pass
+// block = 8 warps; warp w owns output o = blockIdx.x*8 + w; x is staged [rows][256] in shared memory so that it is
+// read from L2 once per block instead of once per warp.
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, long long ldx,
+                                                         const float* __restrict__ W, const float* __restrict__ bias,
+                                                         float scale, float bias_mul, int act, float* __restrict__ y,
+                                                         int B, int I, int O) {
+  __shared__ float xs[LF_BMAX][LF_IC + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * LF_OB + warp;
+  const float* w = W + (size_t)(o < O ? o : 0) * I;
+  for (int b0 = 0; b0 < B; b0 += LF_BMAX) {
+    const int nb = (B - b0 < LF_BMAX) ? (B - b0) : LF_BMAX;
+    float acc[LF_BMAX];
 #pragma unroll
-    for (int j = 0; j < LIN_BB; ++j) acc[j] = 0.f;
-    for (int i = lane; i < I; i += 32) {
-      float wv = w[i];
+    for (int j = 0; j < LF_BMAX; ++j) acc[j] = 0.f;
+    for (int i0 = 0; i0 < I; i0 += LF_IC) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < nb * LF_IC; t += blockDim.x) {
+        int r = t / LF_IC, c = t % LF_IC;
+        xs[r][c] = (i0 + c < I) ? x[(size_t)(b0 + r) * ldx + i0 + c] : 0.f;
+      }
+      __syncthreads();
+      if (o < O) {
 #pragma unroll
-      for (int j = 0; j < LIN_BB; ++j)
-        if (b0 + j < B) acc[j] = fmaf(wv, x[(size_t)(b0 + j) * ldx + i], acc[j]);
+        for (int cc = 0; cc < LF_IC / 32; ++cc) {
+          int c = cc * 32 + lane;
+          float wv = (i0 + c < I) ? w[i0 + c] : 0.f;
+#pragma unroll
+          for (int j = 0; j < LF_BMAX; ++j)
+            if (j < nb) acc[j] = fmaf(wv, xs[j][c], acc[j]);
+        }
+      }
     }
+    if (o < O) {
 #pragma unroll
-    for (int j = 0; j < LIN_BB; ++j) {
-      float s = sg_warp_sum(acc[j]);
-      if (lane == 0 && b0 + j < B) {
-        s = s * scale + (bias ? bias[o] * bias_mul : 0.f);
-        y[(size_t)(b0 + j) * O + o] = act ? sg_lrelu(s) : s;
+      for (int j = 0; j < LF_BMAX; ++j) {
+        if (j < nb) {
+          float s = sg_warp_sum(acc[j]);
+          if (lane == 0) {
+            s = s * scale + (bias ? bias[o] * bias_mul : 0.f);
+            y[(size_t)(b0 + j) * O + o] = act ? sg_lrelu(s) : s;
+          }
+        }
       }
     }
   }
 }
 
-// gx[b][i] = scale * sum_o gy[b][o] * W[o][i]
+// gx[b][i] = scale * sum_o gy[b][o] * W[o][i]; a thread owns column i for up to 32 batch rows, so W is read once.
+constexpr int LD_BB = 32;
 __global__ void linear_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ W, float scale,
                                     float* __restrict__ gx, int B, int I, int O) {
+  __shared__ float gs[LD_BB][64];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= I) return;
-  for (int b0 = blockIdx.y * LIN_BB; b0 < B; b0 += gridDim.y * LIN_BB) {
-    float acc[LIN_BB];
+  for (int b0 = blockIdx.y * LD_BB; b0 < B; b0 += gridDim.y * LD_BB) {
+    const int nb = (B - b0 < LD_BB) ? (B - b0) : LD_BB;
+    float acc[LD_BB];
 #pragma unroll
-    for (int j = 0; j < LIN_BB; ++j) acc[j] = 0.f;
-    for (int o = 0; o < O; ++o) {
-      float wv = W[(size_t)o * I + i];
+    for (int j = 0; j < LD_BB; ++j) acc[j] = 0.f;
+    for (int o0 = 0; o0 < O; o0 += 64) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < nb * 64; t += blockDim.x) {
+        int r = t / 64, c = t % 64;
+        gs[r][c] = (o0 + c < O) ? gy[(size_t)(b0 + r) * O + o0 + c] : 0.f;
+      }
+      __syncthreads();
+      if (i < I) {
+        const int on = (O - o0 < 64) ? (O - o0) : 64;
+        for (int oo = 0; oo < on; ++oo) {
+          float wv = W[(size_t)(o0 + oo) * I + i];
 #pragma unroll
-      for (int j = 0; j < LIN_BB; ++j)
-        if (b0 + j < B) acc[j] = fmaf(wv, gy[(size_t)(b0 + j) * O + o], acc[j]);
+          for (int j = 0; j < LD_BB; ++j)
+            if (j < nb) acc[j] = fmaf(wv, gs[j][oo], acc[j]);
+        }
+      }
     }
+    if (i < I) {
 #pragma unroll
-    for (int j = 0; j < LIN_BB; ++j)
-      if (b0 + j < B) gx[(size_t)(b0 + j) * I + i] = acc[j] * scale;
+      for (int j = 0; j < LD_BB; ++j)
+        if (j < nb) gx[(size_t)(b0 + j) * I + i] = acc[j] * scale;
+    }
   }
 }
 
@@ -293,14 +331,13 @@ __global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float*
 
 SG_EXPORT int sg_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale,
                             float bias_mul, int act, float* y, int B, int I, int O, void* stream) {
-  int warps_per_blk = 4;
-  linear_fwd_kernel<<<sg_cdiv(O, warps_per_blk), warps_per_blk * 32, 0, (cudaStream_t)stream>>>(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O);
+  linear_fwd_kernel<<<sg_cdiv(O, LF_OB), 256, 0, (cudaStream_t)stream>>>(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O);
   return sg_check_launch("sg_linear_fwd");
 }
 
 SG_EXPORT int sg_linear_dgrad(const float* gy, const float* W, float scale, float* gx, int B, int I, int O,
                               void* stream) {
-  dim3 grid(sg_cdiv(I, 128), sg_cdiv(B, LIN_BB));
+  dim3 grid(sg_cdiv(I, 128), sg_cdiv(B, LD_BB));
   linear_dgrad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gy, W, scale, gx, B, I, O);
   return sg_check_launch("sg_linear_dgrad");
 }

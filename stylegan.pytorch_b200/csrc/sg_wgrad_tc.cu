@@ -100,29 +100,35 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_mn(p.BM, p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = t0; tile < t1; ++tile) {
-        mbar_wait(&bars->full[stage], phase);
-        tc_fence_after();
-        const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        const uint32_t sB = sA + a_bytes;
+    // whole warp, warp-uniform state; one elected lane issues (see sg_conv_tc.cu)
+    const uint32_t idesc = make_idesc_bf16_mn(p.BM, p.BN);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      mbar_wait(&bars->full[stage], phase);
+      tc_fence_after();
+      const uint32_t sA = smem_base + (uint32_t)(stage * p.stage_bytes);
+      const uint32_t sB = sA + (uint32_t)a_bytes;
+      const uint64_t a0 = make_desc_mn_sw128(sA, DY_BLOCK_BYTES);
+      const uint64_t b0 = make_desc_mn_sw128(sB, X_BLOCK_BYTES);
+      const uint32_t not_first = (tile != t0) ? 1u : 0u;
+      const bool leader = elect_one_sync();
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
+      for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-          for (int k = 0; k < (TH * TW) / 16; ++k) {            // 8 K-steps of 16 pixels
-            uint64_t ad = make_desc_mn_sw128(sA + k * 2048, DY_BLOCK_BYTES);
-            uint64_t bd = make_desc_mn_sw128(sB + kh * (TW * 128) + k * 2048, X_BLOCK_BYTES);
-            umma_bf16(tmem_base + (uint32_t)(kh * p.BN), ad, bd, idesc, (tile != t0 || k != 0) ? 1u : 0u);
-          }
+        for (int k = 0; k < (TH * TW) / 16; ++k) {            // 8 K-steps of 16 pixels = 2048 B each
+          const uint64_t ad = a0 + (uint64_t)((k * 2048) >> 4);
+          const uint64_t bd = b0 + (uint64_t)((kh * (TW * 128) + k * 2048) >> 4);
+          if (leader) umma_bf16(tmem_base + (uint32_t)(kh * p.BN), ad, bd, idesc, k ? 1u : not_first);
         }
-        umma_commit(&bars->empty[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&bars->done);
+      if (leader) umma_commit(&bars->empty[stage]);
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    if (elect_one_sync()) umma_commit(&bars->done);
+    __syncwarp();
   } else {
     // epilogue: TMEM -> fp32 partials.  M=128: row = 32*q + lane.  M=64: row = 16*q + lane for lane < 16.
     const int q = warp & 3;

@@ -761,8 +761,9 @@ class ToRgb(Function):
             res[1] = ChannelSum.apply(x_hi, g, False, a_hi * s_hi).reshape(W_hi.shape)
         if hb_hi and ctx.needs_input_grad[2]:
             gb = torch.empty((K,), dtype=torch.float32, device=dev)
-            lib.sg_plane_sum(ptr(g), ptr(gb), N, K, H * W, float(a_hi), 0, st)
-            count_launch()
+            ws = torch.empty((K * 64,), dtype=torch.float32, device=dev)
+            lib.sg_plane_sum(ptr(g), ptr(gb), ptr(ws), N, K, H * W, float(a_hi), 0, st)
+            count_launch(2)
             res[2] = gb
         if x_lo is not None:
             Cl = x_lo.shape[-1]
@@ -780,8 +781,9 @@ class ToRgb(Function):
                 res[6] = ChannelSum.apply(x_lo, glo, False, a_lo * s_lo).reshape(W_lo.shape)
             if hb_lo and ctx.needs_input_grad[7]:
                 gb = torch.empty((K,), dtype=torch.float32, device=dev)
-                lib.sg_plane_sum(ptr(g), ptr(gb), N, K, H * W, float(a_lo), 0, st)
-                count_launch()
+                ws = torch.empty((K * 64,), dtype=torch.float32, device=dev)
+                lib.sg_plane_sum(ptr(g), ptr(gb), ptr(ws), N, K, H * W, float(a_lo), 0, st)
+                count_launch(2)
                 res[7] = gb
         return tuple(res)
 

@@ -138,6 +138,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const uint32_t sB = p.resident ? (sW + (uint32_t)((kc * 9 + kw) * b_tap_bytes)) : (sA + A_BYTES);
         const uint64_t a0 = make_desc_sw128(sA);
         const uint64_t b0 = make_desc_sw128(sB);
+        const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
+        const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
         const uint32_t bstep = b_kh_stride >> 4;
         const bool leader = elect_one_sync();
 #pragma unroll
@@ -145,9 +147,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // descriptor start-address field is in 16-byte units: +kh*TW rows of 128 B, +k*32 B inside the atom
-            const uint64_t ad = a0 + (uint64_t)((kh * (TW * 128) + k * 32) >> 4);
-            const uint64_t bd = b0 + (uint64_t)(kh * bstep + ((k * 32) >> 4));
-            if (leader) umma_bf16(tmem_d, ad, bd, idesc, (it | kh | k) ? 1u : 0u);
+            const uint32_t al = a_lo + (uint32_t)((kh * (TW * 128) + k * 32) >> 4);
+            const uint32_t bl = b_lo + kh * bstep + (uint32_t)((k * 32) >> 4);
+            if (leader) umma_bf16_lohi(tmem_d, al, a_hi, bl, b_hi, idesc, (it | kh | k) ? 1u : 0u);
           }
         }
         if (leader) umma_commit(&bars->empty[stage]);          // frees the smem stage once these MMAs have read it

@@ -61,38 +61,36 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
   }
 }
 
-// gx[b][i] = scale * sum_o gy[b][o] * W[o][i]; a thread owns column i for up to 32 batch rows, so W is read once.
+// gx[b][i] = scale * sum_o gy[b][o] * W[o][i].  grid (I/128, O splits): a thread owns column i for up to 32 batch
+// rows over one slice of o, so W is read once and the grid stays wide; slices combine with atomicAdd (gx pre-zeroed).
 constexpr int LD_BB = 32;
+constexpr int LD_OS = 64;     // o values per split
 __global__ void linear_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ W, float scale,
                                     float* __restrict__ gx, int B, int I, int O) {
-  __shared__ float gs[LD_BB][64];
+  __shared__ float gs[LD_BB][LD_OS];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int b0 = blockIdx.y * LD_BB; b0 < B; b0 += gridDim.y * LD_BB) {
+  const int o0 = blockIdx.y * LD_OS;
+  const int on = (O - o0 < LD_OS) ? (O - o0) : LD_OS;
+  for (int b0 = 0; b0 < B; b0 += LD_BB) {
     const int nb = (B - b0 < LD_BB) ? (B - b0) : LD_BB;
-    float acc[LD_BB];
-#pragma unroll
-    for (int j = 0; j < LD_BB; ++j) acc[j] = 0.f;
-    for (int o0 = 0; o0 < O; o0 += 64) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < nb * 64; t += blockDim.x) {
-        int r = t / 64, c = t % 64;
-        gs[r][c] = (o0 + c < O) ? gy[(size_t)(b0 + r) * O + o0 + c] : 0.f;
-      }
-      __syncthreads();
-      if (i < I) {
-        const int on = (O - o0 < 64) ? (O - o0) : 64;
-        for (int oo = 0; oo < on; ++oo) {
-          float wv = W[(size_t)(o0 + oo) * I + i];
-#pragma unroll
-          for (int j = 0; j < LD_BB; ++j)
-            if (j < nb) acc[j] = fmaf(wv, gs[j][oo], acc[j]);
-        }
-      }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nb * LD_OS; t += blockDim.x) {
+      int r = t / LD_OS, c = t % LD_OS;
+      gs[r][c] = (c < on) ? gy[(size_t)(b0 + r) * O + o0 + c] : 0.f;
     }
+    __syncthreads();
     if (i < I) {
+      float acc[LD_BB];
+#pragma unroll
+      for (int j = 0; j < LD_BB; ++j) acc[j] = 0.f;
+      for (int oo = 0; oo < on; ++oo) {
+        float wv = W[(size_t)(o0 + oo) * I + i];
+#pragma unroll
+        for (int j = 0; j < LD_BB; ++j) acc[j] = fmaf(wv, gs[j][oo], acc[j]);
+      }
 #pragma unroll
       for (int j = 0; j < LD_BB; ++j)
-        if (j < nb) gx[(size_t)(b0 + j) * I + i] = acc[j] * scale;
+        if (j < nb) atomicAdd(&gx[(size_t)(b0 + j) * I + i], acc[j] * scale);
     }
   }
 }
@@ -337,8 +335,10 @@ SG_EXPORT int sg_linear_fwd(const float* x, long long ldx, const float* W, const
 
 SG_EXPORT int sg_linear_dgrad(const float* gy, const float* W, float scale, float* gx, int B, int I, int O,
                               void* stream) {
-  dim3 grid(sg_cdiv(I, 128), sg_cdiv(B, LD_BB));
-  linear_dgrad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gy, W, scale, gx, B, I, O);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(gx, 0, (size_t)B * I * sizeof(float), st);
+  dim3 grid(sg_cdiv(I, 128), sg_cdiv(O, LD_OS));
+  linear_dgrad_kernel<<<grid, 128, 0, st>>>(gy, W, scale, gx, B, I, O);
   return sg_check_launch("sg_linear_dgrad");
 }
 

@@ -113,14 +113,16 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_cons
       const uint64_t a0 = make_desc_mn_sw128(sA, DY_BLOCK_BYTES);
       const uint64_t b0 = make_desc_mn_sw128(sB, X_BLOCK_BYTES);
       const uint32_t not_first = (tile != t0) ? 1u : 0u;
+      const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
+      const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
       const bool leader = elect_one_sync();
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
         for (int k = 0; k < (TH * TW) / 16; ++k) {            // 8 K-steps of 16 pixels = 2048 B each
-          const uint64_t ad = a0 + (uint64_t)((k * 2048) >> 4);
-          const uint64_t bd = b0 + (uint64_t)((kh * (TW * 128) + k * 2048) >> 4);
-          if (leader) umma_bf16(tmem_base + (uint32_t)(kh * p.BN), ad, bd, idesc, k ? 1u : not_first);
+          const uint32_t al = a_lo + (uint32_t)((k * 2048) >> 4);
+          const uint32_t bl = b_lo + (uint32_t)((kh * (TW * 128) + k * 2048) >> 4);
+          if (leader) umma_bf16_lohi(tmem_base + (uint32_t)(kh * p.BN), al, a_hi, bl, b_hi, idesc, k ? 1u : not_first);
         }
       }
       if (leader) umma_commit(&bars->empty[stage]);

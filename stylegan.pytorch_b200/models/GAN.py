@@ -389,10 +389,19 @@ class StyleGAN:
             with torch.no_grad():
                 real_samples = self.__progressive_down_sampling(real_batch, depth, alpha)
         fake_samples = self.gen(noise, depth, alpha, labels)
-        if not self.conditional:
-            loss = self.loss.gen_loss(real_samples, fake_samples, depth, alpha)
-        else:
-            loss = self.loss.gen_loss(real_samples, fake_samples, labels, depth, alpha)
+        # the discriminator is a fixed function in this step: with requires_grad off its layers compute input
+        # gradients only (the reference computes, and then discards, all discriminator weight gradients here)
+        d_params = [p for p in self.dis.parameters() if p.requires_grad]
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            if not self.conditional:
+                loss = self.loss.gen_loss(real_samples, fake_samples, depth, alpha)
+            else:
+                loss = self.loss.gen_loss(real_samples, fake_samples, labels, depth, alpha)
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
         self.gen_optim.zero_grad()
         # only generator parameters need gradients here (the reference also accumulates unused D gradients)
         g_params = [p for p in self.gen.parameters() if p.requires_grad]

@@ -107,9 +107,10 @@ class LogisticGAN(GANLoss):
         """sum over the batch of |d D(real) / d real|^2, with the graph kept for the second backward."""
         real_img = real_img.detach().requires_grad_(True)
         real_logit = self.dis(real_img, height, alpha)
-        real_grads = torch.autograd.grad(outputs=real_logit, inputs=real_img,
-                                         grad_outputs=torch.ones_like(real_logit), create_graph=True,
-                                         retain_graph=True)[0]
+        with _ops.skip_param_grads():        # only d/d(image) is wanted from this backward
+            real_grads = torch.autograd.grad(outputs=real_logit, inputs=real_img,
+                                             grad_outputs=torch.ones_like(real_logit), create_graph=True,
+                                             retain_graph=True)[0]
         return _ops.SqSum.apply(real_grads, 1.0).reshape(())
 
     def dis_loss(self, real_samps, fake_samps, height, alpha, r1_gamma=10.0):

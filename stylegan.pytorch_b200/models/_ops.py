@@ -16,7 +16,24 @@ from torch.autograd.function import once_differentiable
 from . import _geom
 from ._lib import lib, ptr, stream, code, count_launch, F32
 
-_state = {"dtype": torch.float32, "use_tc": True}
+_state = {"dtype": torch.float32, "use_tc": True, "skip_param_grads": False}
+
+
+class skip_param_grads:
+    """Context manager for a backward pass whose parameter gradients are not wanted (the first, create_graph=True
+    backward of the R1 penalty differentiates wrt the image only).  autograd cannot tell a custom Function which of
+    its gradient outputs will be consumed, so without this every layer would also compute a weight gradient there."""
+
+    def __enter__(self):
+        self._old = _state["skip_param_grads"]
+        _state["skip_param_grads"] = True
+
+    def __exit__(self, *a):
+        _state["skip_param_grads"] = self._old
+
+
+def _want_params():
+    return not _state["skip_param_grads"]
 
 
 def set_precision(p):
@@ -148,7 +165,7 @@ class Conv(Function):
         gx = gW = None
         if ctx.needs_input_grad[0]:
             gx = Conv.apply(gy, W, kind, "dgrad" if direction == "fwd" else "fwd", scale)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _want_params():
             gW = ConvWgrad.apply(x, gy, kind, scale, W.shape) if direction == "fwd" else \
                 ConvWgrad.apply(gy, x, kind, scale, W.shape)
         return gx, gW, None, None, None
@@ -207,9 +224,10 @@ class ConvBiasAct(Function):
         kind, scale, bias_mul, act, has_bias = ctx.cfg
         g = LreluBwd.apply(gy, y) if act else gy
         gx = Conv.apply(g, W, kind, "dgrad", scale) if ctx.needs_input_grad[0] else None
-        gW = ConvWgrad.apply(x, g, kind, scale, W.shape) if ctx.needs_input_grad[1] else None
+        wp = _want_params()
+        gW = ConvWgrad.apply(x, g, kind, scale, W.shape) if (ctx.needs_input_grad[1] and wp) else None
         gb = None
-        if has_bias and ctx.needs_input_grad[2]:
+        if has_bias and ctx.needs_input_grad[2] and wp:
             gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1)
         return gx, gW, gb, None, None, None, None
 
@@ -282,7 +300,8 @@ class Blur(Function):
     def backward(ctx, g):
         has_bias, bias_mul = ctx.cfg
         gx = Blur.apply(g, None, 1.0) if ctx.needs_input_grad[0] else None
-        gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1) if (has_bias and ctx.needs_input_grad[1]) else None
+        gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1) \
+            if (has_bias and ctx.needs_input_grad[1] and _want_params()) else None
         return gx, gb, None
 
 
@@ -356,7 +375,7 @@ class RgbIn(Function):
         g = LreluBwd.apply(gy, y) if act else gy
         gimg = RgbInDgrad.apply(g, W, scale) if ctx.needs_input_grad[0] else None
         gW = gb = None
-        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+        if (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])) and _want_params():
             rows = ChannelSum.apply(g, img, True, 1.0)           # [K+1, C]
             K = img.shape[1]
             if ctx.needs_input_grad[1]:
@@ -470,7 +489,7 @@ class Linear(Function):
         g = LreluBwd.apply(gy, y) if act else gy
         gx = LinearDgrad.apply(g, W, scale) if ctx.needs_input_grad[0] else None
         gW = gb = None
-        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+        if (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])) and _want_params():
             gW, gb = LinearWgrad.apply(g, x, scale, bias_mul, has_bias)
         return gx, gW, (gb if has_bias else None), None, None, None
 
@@ -951,7 +970,7 @@ class PoolNHWC(Function):
         g = LreluBwd.apply(gy, y) if act else gy
         gx = UpNHWC.apply(g, scale) if ctx.needs_input_grad[0] else None
         gb = None
-        if has_bias and ctx.needs_input_grad[1]:
+        if has_bias and ctx.needs_input_grad[1] and _want_params():
             gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1)
         return gx, gb, None, None, None
 

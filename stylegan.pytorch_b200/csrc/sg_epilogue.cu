@@ -76,6 +76,99 @@ __global__ void epi_reduce_kernel(const T* __restrict__ in0, const T* __restrict
   }
 }
 
+// Vectorised variant: a thread owns one 16-byte channel vector and strides over the pixels of its chunk.
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) epi_reduce_vec_kernel(const T* __restrict__ in0, const T* __restrict__ in1,
+                                                             T* __restrict__ zout, const float* __restrict__ bias,
+                                                             float bias_mul, const float* __restrict__ noise,
+                                                             const float* __restrict__ noise_w,
+                                                             const float* __restrict__ mr, double* __restrict__ sums,
+                                                             int HW, int C, int pix_per_blk, int act) {
+  using V = SgVec<T>;
+  extern __shared__ float sm[];  // [2][PR][C]
+  const int CV = C / V::N;
+  const int PR = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, pr = threadIdx.x / CV;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_blk;
+  int p1 = p0 + pix_per_blk;
+  if (p1 > HW) p1 = HW;
+  const size_t base = (size_t)n * HW;
+  if (pr < PR) {
+    float s0[V::N], s1[V::N], b[V::N], nw[V::N], a0[V::N], a1[V::N];   // a0/a1: pivot (MODE 0) or mean/rstd (MODE 1)
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) {
+      const int c = cv * V::N + k;
+      s0[k] = s1[k] = 0.f;
+      if (MODE == 0) {
+        b[k] = bias ? bias[c] * bias_mul : 0.f;
+        nw[k] = (noise && noise_w) ? noise_w[c] : 0.f;
+      } else {
+        a0[k] = mr[((size_t)n * C + c) * 2 + 0];
+        a1[k] = mr[((size_t)n * C + c) * 2 + 1];
+      }
+    }
+    if (MODE == 0) {
+      V v0;
+      v0.load(in0 + base * C + cv * V::N);
+      const float nz0 = noise ? noise[base] : 0.f;
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) {
+        float v = v0.get(k) + b[k];
+        if (noise) v = fmaf(nw[k], nz0, v);
+        if (act) v = sg_lrelu(v);
+        a0[k] = sg_to_f(sg_from_f<T>(v));
+        if (blockIdx.x == 0 && pr == 0) sums[((size_t)n * C + cv * V::N + k) * 3 + 2] = (double)a0[k];
+      }
+    }
+    for (int p = p0 + pr; p < p1; p += PR) {
+      const size_t idx = (base + p) * C + cv * V::N;
+      if (MODE == 0) {
+        V vi, vo;
+        vi.load(in0 + idx);
+        const float nz = noise ? noise[base + p] : 0.f;
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) {
+          float v = vi.get(k) + b[k];
+          if (noise) v = fmaf(nw[k], nz, v);
+          if (act) v = sg_lrelu(v);
+          vo.set(k, v);
+        }
+        vo.store(zout + idx);
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) {
+          float zr = vo.get(k) - a0[k];
+          s0[k] += zr;
+          s1[k] = fmaf(zr, zr, s1[k]);
+        }
+      } else {
+        V vg, vz;
+        vg.load(in0 + idx);
+        vz.load(in1 + idx);
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) {
+          float g = vg.get(k);
+          float xh = (vz.get(k) - a0[k]) * a1[k];
+          s0[k] += g;
+          s1[k] = fmaf(g, xh, s1[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) {
+      sm[((size_t)0 * PR + pr) * C + cv * V::N + k] = s0[k];
+      sm[((size_t)1 * PR + pr) * C + cv * V::N + k] = s1[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    int j = i / C, c = i % C;
+    float s = 0.f;
+    for (int r = 0; r < PR; ++r) s += sm[((size_t)j * PR + r) * C + c];
+    atomicAdd(&sums[((size_t)n * C + c) * 3 + j], (double)s);
+  }
+}
+
 // per-(n,c): mean/rstd and the fused affine (a, d).  style = [N, 2C] (s0 | s1); style may be null (plain IN).
 __global__ void epi_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ style,
                                     float* __restrict__ mr, float* __restrict__ ab, int N, int C, int HW, float eps) {
@@ -181,6 +274,13 @@ int launch_reduce(const void* in0, const void* in1, void* zout, const float* bia
   size_t smem = (size_t)2 * EPI_ROWS * C * sizeof(float);
   if (smem > 48 * 1024) { sg_set_error("epilogue: C too large"); return 1000; }
   dim3 grid(chunks, N);
+  const int VN = SgVec<T>::N;
+  if (C % VN == 0 && C / VN <= 256 && (size_t)2 * (256 / (C / VN)) * C * sizeof(float) <= 48 * 1024) {
+    size_t smv = (size_t)2 * (256 / (C / VN)) * C * sizeof(float);
+    epi_reduce_vec_kernel<T, MODE><<<grid, 256, smv, st>>>((const T*)in0, (const T*)in1, (T*)zout, bias, bias_mul,
+                                                           noise, noise_w, mr, sums, HW, C, pix_per_blk, act);
+    return sg_check_launch("epi_reduce_vec");
+  }
   epi_reduce_kernel<T, MODE><<<grid, block, smem, st>>>((const T*)in0, (const T*)in1, (T*)zout, bias, bias_mul, noise,
                                                         noise_w, mr, sums, HW, C, pix_per_blk, act);
   return sg_check_launch("epi_reduce");

@@ -85,6 +85,9 @@ int sg_bias_noise(const void* x, const float* bias, float bias_mul, const float*
 int sg_up2_nhwc(const void* x, void* y, float scale, int dtype, int N, int H, int W, int C, void* stream);
 int sg_pool2_nhwc(const void* x, void* y, const float* bias, float bias_mul, int act, float scale, int dtype, int N,
                   int Ho, int Wo, int C, void* stream);
+/* Zero-pad or crop an NHWC map to [N,hd,wd,C] (runs the 4x4/8x8 layers on the 8x16 tensor-core tiles). */
+int sg_pad_crop_nhwc(const void* src, void* dst, int dtype, int N, int hs, int ws, int hd, int wd, int C,
+                     void* stream);
 /* out = a*x + b*y (y may be NULL): fade-in lerps GAN.py:202,427,586; scaling. */
 int sg_axpby(const void* x, const void* y, void* out, float a, float b, long long n, int dtype, void* stream);
 /* LeakyReLU(0.2) backward from the activation output (GAN.py:68,151,347). */

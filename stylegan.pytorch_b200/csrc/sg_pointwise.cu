@@ -578,6 +578,29 @@ __global__ void pool2_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, co
   }
 }
 
+// dst[n, y, x, :] = (y < hs && x < ws) ? src[n, y, x, :] : 0 -- zero-pad (dst larger) or crop (dst smaller) of an NHWC
+// map.  Used to run the 4x4 / 8x8 layers on the 8x16-pixel tiles of the tensor-core kernels.
+template <class T>
+__global__ void pad_crop_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int hs, int ws, int hd,
+                                     int wd, int C) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const long long total = (long long)N * hd * wd * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int x = (int)(p % wd);
+    long long r = p / wd;
+    int y = (int)(r % hd);
+    int n = (int)(r / hd);
+    V v;
+    if (y < hs && x < ws) v.load(src + (((size_t)n * hs + y) * ws + x) * C + cv * V::N);
+    else v.zero();
+    v.store(dst + (size_t)p * C + cv * V::N);
+  }
+}
+
 // y = x + bias[c]*bias_mul + noise_w[c]*noise[n,p]   (stand-alone NoiseLayer / bias add; CustomLayers.py:191-200,178)
 template <class T>
 __global__ void bias_noise_kernel(const T* __restrict__ x, const float* __restrict__ bias, float bias_mul,
@@ -804,4 +827,15 @@ SG_EXPORT int sg_pool2_nhwc(const void* x, void* y, const float* bias, float bia
     pool2_nhwc_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)x, (T*)y, bias, bias_mul, act, scale, N, Ho, Wo, C);
   });
   return sg_check_launch("sg_pool2_nhwc");
+}
+
+SG_EXPORT int sg_pad_crop_nhwc(const void* src, void* dst, int dtype, int N, int hs, int ws, int hd, int wd, int C,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    SG_REQUIRE(C % SgVec<T>::N == 0, "sg_pad_crop_nhwc: C must be a multiple of the 16-byte vector width");
+    long long total = (long long)N * hd * wd * (C / SgVec<T>::N);
+    pad_crop_nhwc_kernel<T><<<sg_grid_1d(total, 256, 148 * 16), 256, 0, st>>>((const T*)src, (T*)dst, N, hs, ws, hd, wd, C);
+  });
+  return sg_check_launch("sg_pad_crop_nhwc");
 }

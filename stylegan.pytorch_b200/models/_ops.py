@@ -975,15 +975,65 @@ class PoolNHWC(Function):
         return gx, gb, None, None, None
 
 
+class PadCrop(Function):
+    """Zero-pad / crop an NHWC map to (H, W) (top-left anchored).  Linear and self-adjoint up to the shape swap."""
+
+    @staticmethod
+    def forward(ctx, x, H, W):
+        _require_cuda(x)
+        x = _c(x)
+        N, h, w, C = x.shape
+        y = torch.empty((N, H, W, C), dtype=x.dtype, device=x.device)
+        lib.sg_pad_crop_nhwc(ptr(x), ptr(y), code(x.dtype), N, h, w, H, W, C, stream())
+        count_launch()
+        ctx.src = (h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return PadCrop.apply(g, ctx.src[0], ctx.src[1]), None, None
+
+
+def _tc_small_ok(x, W):
+    """4x4 / 8x8 (or 8-wide) maps: run on the tensor-core kernels inside a zero-padded 8x16 frame."""
+    co, ci, k, _ = W.shape
+    if x.dtype != torch.bfloat16 or not _state["use_tc"] or k != 3:
+        return False
+    N, H, Wd, _ = x.shape
+    if H > 8 or Wd > 8 or (H >= 8 and Wd >= 16):
+        return False
+    from . import _tc
+    return _tc.conv_and_wgrad_supported(N, 8, 16, ci, co)
+
+
+def _conv_same_padded(x, W, bias, kind, scale, bias_mul, act):
+    N, H, Wd, _ = x.shape
+    xp = PadCrop.apply(x, 8, 16)
+    if bias is None and not act:
+        yp = Conv.apply(xp, W, kind, "fwd", scale)
+    else:
+        yp = ConvBiasAct.apply(xp, W, bias, kind, scale, bias_mul, act)
+    return PadCrop.apply(yp, H, Wd)
+
+
 def conv_layer(x, W, bias, kind, scale, bias_mul, act):
     """One EqualizedConv2d evaluation on NHWC activations.  In bf16 mode the up/down-sampling convolutions run as
     the reference's unfused formulation (nearest-up -> conv3x3, conv3x3 -> 2x2 box; CustomLayers.py:153-154,166-176)
     so that all their FLOPs are on the tcgen05 3x3 kernels; otherwise as one tap-merged convolution."""
     co, ci, k, _ = W.shape
+    if kind in ("same", "same_flip") and _tc_small_ok(x, W):
+        return _conv_same_padded(x, W, bias, kind, scale, bias_mul, act)
     if kind in ("up", "up_fused", "down") and x.dtype == torch.bfloat16 and _state["use_tc"] and k == 3:
         from . import _tc
         N, H, Wd, _ = x.shape
         Hh, Wh = (2 * H, 2 * Wd) if kind != "down" else (H, Wd)
+        if Hh <= 8 and Wh <= 8 and _tc.conv_and_wgrad_supported(N, 8, 16, ci, co):
+            # tiny maps: same composition inside the padded 8x16 frame
+            if kind == "down":
+                y = _conv_same_padded(x, W, None, "same", scale, 1.0, False)
+                return PoolNHWC.apply(y, bias, bias_mul, act, 0.25)
+            k2 = "same" if kind == "up" else "same_flip"
+            return _conv_same_padded(UpNHWC.apply(x, 1.0), W, bias, k2, scale, bias_mul, act)
         if _tc.conv_and_wgrad_supported(N, Hh, Wh, ci, co):
             if kind == "down":
                 y = Conv.apply(x, W, "same", "fwd", scale)

@@ -84,7 +84,8 @@ def test_wgrad3x3_tc_matches_oracle(N, H, W, ci, co):
 
 
 @pytest.mark.parametrize("kind,ci,co,hw", [("up", 128, 64, 16), ("up_fused", 128, 64, 64), ("down", 64, 128, 32),
-                                            ("down", 64, 128, 128)])
+                                            ("down", 64, 128, 128), ("same", 128, 128, 4), ("same", 64, 128, 8),
+                                            ("up", 128, 128, 4), ("down", 128, 64, 8)])
 def test_up_down_layers_on_tensor_cores(kind, ci, co, hw):
     """bf16 up/down EqualizedConv2d layers (nearest-up -> tc conv, tc conv -> box pool) vs the oracle, fwd + grads."""
     from models import _ops

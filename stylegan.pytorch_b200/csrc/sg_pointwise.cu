@@ -260,7 +260,8 @@ __global__ void partial_reduce_kernel(const float* __restrict__ part, int nblk, 
 // from_rgb: img fp32 NCHW [N,K,H,W] -> y NHWC T [N,H,W,C]:  y = act(scale * sum_k W[c][k] img[k] + b[c]*bmul)
 // reference GAN.py:358,377 (1x1 EqualizedConv2d) + LeakyReLU.  K <= 4.
 // ---------------------------------------------------------------------------------------------------------
-// vectorised: one thread = one pixel x 16-byte channel vector
+// vectorised: one thread = one pixel x 16-byte channel vector.  The launch makes gridDim*blockDim a multiple of CV,
+// so a thread keeps the same channel vector for its whole grid-stride loop and holds its weights in registers.
 template <class T>
 __global__ void rgb_in_vec_kernel(const float* __restrict__ img, const float* __restrict__ Wt,
                                   const float* __restrict__ bias, float scale, float bias_mul, int act,
@@ -268,21 +269,30 @@ __global__ void rgb_in_vec_kernel(const float* __restrict__ img, const float* __
   using V = SgVec<T>;
   const int CV = C / V::N;
   const long long total = (long long)N * HW * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = (int)(i0 % CV);
+  float wr[V::N][4], br[V::N];
+#pragma unroll
+  for (int e = 0; e < V::N; ++e) {
+    const int c = cv * V::N + e;
+    br[e] = bias ? bias[c] * bias_mul : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wr[e][k] = (k < K) ? Wt[c * K + k] * scale : 0.f;
+  }
+  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long p = i / CV;
     long long n = p / HW;
     int hw = (int)(p - n * HW);
     float px[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < K; ++k) px[k] = img[((size_t)n * K + k) * HW + hw];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < K) px[k] = img[((size_t)n * K + k) * HW + hw];
     V o;
 #pragma unroll
     for (int e = 0; e < V::N; ++e) {
-      int c = cv * V::N + e;
-      float s = 0.f;
-      for (int k = 0; k < K; ++k) s = fmaf(Wt[c * K + k], px[k], s);
-      s = s * scale + (bias ? bias[c] * bias_mul : 0.f);
+      float s = br[e];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s = fmaf(wr[e][k], px[k], s);
       if (act) s = sg_lrelu(s);
       o.set(e, s);
     }
@@ -721,7 +731,7 @@ SG_EXPORT int sg_rgb_in(const float* img, const float* W, const float* bias, flo
   cudaStream_t st = (cudaStream_t)stream;
   long long total = (long long)N * HW * C;
   SG_DISPATCH(dtype, {
-    if (C % SgVec<T>::N == 0)
+    if (C % SgVec<T>::N == 0 && 256 % (C / SgVec<T>::N) == 0)     // 256 threads per block, CV | 256 -> fixed cv per thread
       rgb_in_vec_kernel<T><<<sg_grid_1d(total / SgVec<T>::N, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);
     else
       rgb_in_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);

@@ -103,11 +103,26 @@ class DiscriminatorTop(nn.Sequential):
         super().__init__(OrderedDict(layers))
 
     def forward_nhwc(self, x):
-        if x.dtype != torch.float32:
-            x = _ops.Cast.apply(x, torch.float32)
-        if hasattr(self, "stddev_layer"):
-            x = self.stddev_layer.forward_nhwc(x)
-        x = self.conv.conv_nhwc(x, with_bias=True, act=True)
+        conv = self.conv
+        b_mul = conv.b_mul if conv.bias is not None else 1.0
+        if hasattr(self, "stddev_layer") and conv.weight.shape[1] == x.shape[-1] + 1 and x.shape[-1] % 64 == 0:
+            # conv over [x, stddev] = conv_x(x) + conv_s(stddev): the 513-channel kernel is split so that the wide
+            # part keeps the vector / tensor-core path (an odd channel count would force the scalar kernel) and only
+            # the single stddev channel goes through the generic one.  Same arithmetic, summed in fp32.
+            c = x.shape[-1]
+            xf = x if x.dtype == torch.float32 else _ops.Cast.apply(x, torch.float32)
+            std = self.stddev_layer.forward_nhwc(xf)[..., c:].contiguous()
+            main = _ops.conv_layer(x, conv.weight[:, :c], None, "same", conv.w_mul, 1.0, False)
+            if main.dtype != torch.float32:
+                main = _ops.Cast.apply(main, torch.float32)
+            extra = _ops.Conv.apply(std, conv.weight[:, c:], "same", "fwd", conv.w_mul)
+            x = _ops.BiasNoise.apply(_ops.Axpby.apply(main, extra, 1.0, 1.0), conv.bias, b_mul, None, None, True)
+        else:
+            if x.dtype != torch.float32:
+                x = _ops.Cast.apply(x, torch.float32)
+            if hasattr(self, "stddev_layer"):
+                x = self.stddev_layer.forward_nhwc(x)
+            x = conv.conv_nhwc(x, with_bias=True, act=True)
         x = x.permute(0, 3, 1, 2).reshape(x.shape[0], -1)       # flatten in the reference's NCHW feature order
         x = self.dense0(x, act=True)
         return self.dense1(x)

@@ -137,7 +137,10 @@ def northstar_kernel_roofline(batch, res, ch, iters=20):
             "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4),
             "peak_source": how + " (burst cuBLAS bf16; kernel timed alone)", "ms_per_launch": round(ms, 4),
             "algorithmic_gflop_per_launch": round(flops / 1e9, 1),
-            "hbm_gbs_algorithmic": round(alg_bytes / (ms * 1e-3) / 1e9, 1), "traffic": None}
+            "hbm_gbs_algorithmic": round(alg_bytes / (ms * 1e-3) / 1e9, 1),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
+            # (profiles/r01_summary.md); the algorithmic minimum is 537 MB
+            "traffic": 487.7e6 if (batch, res, ch) == (32, 256, 64) else None, "traffic_unit": "bytes/launch"}
 
 
 def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):

@@ -1,0 +1,149 @@
+"""Wider coverage of the drop-in networks on the GPU: every depth and fade-in alpha, 'fixed' structure, eval mode,
+the non-default losses, conditional mode, checkpoint round trip (the pyramid the reference lacks)."""
+import io
+import random
+
+import pytest
+import torch
+
+import stylegan_oracle as O
+from test_gpu_networks import FixedMixing, build, rel, set_noise
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _fp32():
+    import models
+    from models import _ops
+    _ops.clear_weight_cache()
+    models.set_precision("fp32")
+    yield
+    models.set_precision("fp32")
+
+
+def _init(arch, seed=0, batch=4):
+    gen = torch.Generator().manual_seed(seed)
+    g_sd, d_sd = O.init_generator(arch, gen), O.init_discriminator(arch, gen)
+    for k in list(g_sd) + list(d_sd):
+        sd = g_sd if k in g_sd else d_sd
+        if k.endswith("noise.weight") or (k.endswith(".bias") and "init_block.bias" not in k):
+            sd[k] = 0.3 * torch.randn(sd[k].shape, generator=gen)
+    return g_sd, d_sd, gen
+
+
+@pytest.mark.parametrize("depth,alpha", [(0, 1.0), (1, 0.0), (1, 0.5), (2, 1.0), (3, 0.25), (4, 0.5), (5, 0.75)])
+def test_every_depth_and_alpha_vs_oracle(depth, alpha):
+    arch = O.Arch(128, latent_size=32, mapping_fmaps=32, mapping_layers=2, fmap_base=512, fmap_max=32)
+    g_sd, d_sd, gen = _init(arch)
+    B = 4
+    noises = [torch.randn(s, generator=gen) for s in O.noise_shapes(arch, B, depth)]
+    z = torch.randn(B, arch.latent_size, generator=gen)
+    z2 = torch.randn(B, arch.latent_size, generator=gen)
+    cutoff = 1 + depth
+    res = 2 ** (depth + 2)
+    real = torch.randn(B, 3, res, res, generator=gen)
+    sd_g = {k: v.clone() for k, v in g_sd.items()}
+    fake_ref = O.generator_forward(sd_g, z, depth, alpha, arch, z2=z2, mixing_cutoff=cutoff, noises=noises)
+    logit_ref = O.discriminator(d_sd, real, depth, alpha, arch)
+    g, d = build(arch, g_sd, d_sd)
+    g.train()
+    set_noise(g, noises)
+    with FixedMixing(z2, cutoff, depth):
+        fake = g(z.to(DEV), depth, alpha)
+    assert fake.shape == fake_ref.shape and fake.dtype == torch.float32
+    assert rel(fake, fake_ref) < 1e-3
+    assert rel(d(real.to(DEV), depth, alpha), logit_ref) < 1e-3
+    # progressive down-sampling of the real batch (reference GAN.py:557-589)
+    from models.GAN import StyleGAN
+    full = torch.randn(B, 3, 128, 128, generator=gen)
+    sg = StyleGAN.__new__(StyleGAN)
+    sg.structure, sg.depth = "linear", arch.depth
+    got = sg._StyleGAN__progressive_down_sampling(full.to(DEV), depth, alpha)
+    assert rel(got, O.progressive_down_sampling(full, arch, depth, alpha)) < 1e-5
+
+
+def test_fixed_structure_and_eval_mode():
+    arch = O.Arch(32, latent_size=32, mapping_fmaps=32, mapping_layers=2, fmap_base=256, fmap_max=32,
+                  structure="fixed")
+    g_sd, d_sd, gen = _init(arch, seed=3)
+    B = 4
+    depth = arch.depth - 1
+    noises = [torch.randn(s, generator=gen) for s in O.noise_shapes(arch, B, depth)]
+    z = torch.randn(B, arch.latent_size, generator=gen)
+    g, d = build(arch, g_sd, d_sd)
+    g.eval()                       # eval: no style mixing, no truncation, no avg update (reference GAN.py:274)
+    set_noise(g, noises)
+    avg0 = g.truncation.avg_latent.clone()
+    fake = g(z.to(DEV), depth, 1.0)
+    fake_ref = O.generator_forward({k: v.clone() for k, v in g_sd.items()}, z, depth, 1.0, arch, training=False,
+                                   noises=noises)
+    assert rel(fake, fake_ref) < 1e-3
+    assert torch.equal(g.truncation.avg_latent, avg0)
+    assert rel(d(fake_ref.to(DEV), depth, 1.0), O.discriminator(d_sd, fake_ref, depth, 1.0, arch)) < 1e-3
+    with pytest.raises(AssertionError):
+        g.g_synthesis(torch.zeros(B, arch.num_layers, 512, device=DEV), depth=arch.depth)
+
+
+@pytest.mark.parametrize("loss_name", ["hinge", "relativistic-hinge"])
+def test_other_losses_vs_oracle(loss_name):
+    from models import Losses
+    arch = O.Arch(16, latent_size=32, mapping_fmaps=32, mapping_layers=2, fmap_base=128, fmap_max=32)
+    g_sd, d_sd, gen = _init(arch, seed=5)
+    B, depth, alpha = 4, 2, 0.5
+    real = torch.randn(B, 3, 16, 16, generator=gen)
+    fake = torch.randn(B, 3, 16, 16, generator=gen)
+    g, d = build(arch, g_sd, d_sd)
+    cls = {"hinge": Losses.HingeGAN, "relativistic-hinge": Losses.RelativisticAverageHingeGAN}[loss_name]
+    L = cls(d)
+    dl = L.dis_loss(real.to(DEV), fake.to(DEV), depth, alpha)
+    gl = L.gen_loss(real.to(DEV), fake.to(DEV), depth, alpha)
+    if loss_name == "hinge":
+        dl_o, gl_o = O.d_loss_hinge(d_sd, real, fake, depth, alpha, arch), O.g_loss_hinge(d_sd, fake, depth, alpha, arch)
+    else:
+        dl_o = O.d_loss_rahinge(d_sd, real, fake, depth, alpha, arch)
+        gl_o = O.g_loss_rahinge(d_sd, real, fake, depth, alpha, arch)
+    assert abs(float(dl) - float(dl_o)) < 1e-3 * abs(float(dl_o)) + 1e-5
+    assert abs(float(gl) - float(gl_o)) < 1e-3 * abs(float(gl_o)) + 1e-5
+    grads = torch.autograd.grad(dl, [p for p in d.parameters()], allow_unused=True)
+    assert any(gr is not None and float(gr.abs().sum()) > 0 for gr in grads)
+
+
+def test_conditional_mode_runs_and_checkpoint_roundtrip(tmp_path):
+    """Conditional G/D (class embedding concatenation, reference GAN.py:233-236,326-369) and the five checkpoint files."""
+    from models.GAN import StyleGAN
+    torch.manual_seed(0)
+    random.seed(0)
+    opt = dict(learning_rate=0.003, beta_1=0, beta_2=0.99, eps=1e-8)
+    g_args = dict(latent_size=32, mapping_fmaps=32, mapping_layers=2, fmap_base=128, fmap_max=32, blur_filter=[1, 2, 1])
+    d_args = dict(fmap_base=128, fmap_max=32, blur_filter=[1, 2, 1])
+    sg = StyleGAN("linear", 16, 3, 32, g_args, d_args, opt, dict(opt), conditional=True, n_classes=5,
+                  loss="conditional-loss", use_ema=True, device=torch.device(DEV))
+    B, depth, alpha = 4, 1, 0.5
+    labels = torch.tensor([0, 1, 2, 4], device=DEV)
+    img = torch.randn(B, 3, 16, 16, device=DEV)
+    z = torch.randn(B, 32, device=DEV)
+    dl = sg.optimize_discriminator(z, img, depth, alpha, labels)
+    gl = sg.optimize_generator(z, img, depth, alpha, labels)
+    assert dl == dl and gl == gl                      # finite
+    # checkpoint layout (reference GAN.py:806-823): plain state_dicts that load back strictly
+    files = {}
+    for name, obj in (("GEN", sg.gen), ("DIS", sg.dis), ("GEN_SHADOW", sg.gen_shadow), ("GEN_OPTIM", sg.gen_optim),
+                      ("DIS_OPTIM", sg.dis_optim)):
+        f = tmp_path / ("GAN_%s_1_1.pth" % name)
+        torch.save(obj.state_dict(), f)
+        files[name] = f
+    sg2 = StyleGAN("linear", 16, 3, 32, g_args, d_args, opt, dict(opt), conditional=True, n_classes=5,
+                   loss="conditional-loss", use_ema=True, device=torch.device(DEV))
+    sg2.gen.load_state_dict(torch.load(files["GEN"]))
+    sg2.dis.load_state_dict(torch.load(files["DIS"]))
+    sg2.gen_shadow.load_state_dict(torch.load(files["GEN_SHADOW"]))
+    sg2.gen_optim.load_state_dict(torch.load(files["GEN_OPTIM"]))
+    sg2.dis_optim.load_state_dict(torch.load(files["DIS_OPTIM"]))
+    for a, b in zip(sg.gen.parameters(), sg2.gen.parameters()):
+        assert torch.equal(a, b)
+    p0 = next(iter(sg2.dis_optim.state))
+    assert float(sg2.dis_optim.state[p0]["step"]) >= 0
+    # and training continues from the restored state
+    sg2.optimize_discriminator(z, img, depth, alpha, labels)

@@ -66,6 +66,14 @@ int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout);
 int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float* bias, float bias_mul, int act, int N, int H,
                   int W, int Cin, int Cout, void* stream);
 
+/* tcgen05/TMA up-/down-sampling convolutions in the tap-merged low-resolution form (csrc/sg_convud_tc.cu):
+ * mode 0 UP   x [N,H,W,Cin] -> y [N,2H,2W,Cout], 4 phases x 2x2 taps  (CustomLayers.py:143-154 upscale conv; dgrad of down)
+ * mode 1 DOWN x [N,2H,2W,Cin] -> y [N,H,W,Cout], 4x4 taps stride 2    (CustomLayers.py:156-180 downscale conv; dgrad of up)
+ * E [16][Cout][Cin] bf16 from sg_wprep_fwd with the tables of models/_geom.py; fused bias + LeakyReLU. */
+int sg_convud_tc_supported(int mode, int N, int H, int W, int Cin, int Cout);
+int sg_convud_tc(int mode, const void* x, const void* E, void* y, const float* bias, float bias_mul, int act, int N,
+                 int H, int W, int Cin, int Cout, void* stream);
+
 /* tcgen05/TMA weight gradient of the same convolution: part [S][9][Cout][Cin] float32 partial sums over S pixel splits
  * (S = sg_wgrad3x3_tc_splits); reduce + scale + OIHW layout with sg_wprep_bwd(transpose=1).  x [N,H,W,Cin], dy
  * [N,H,W,Cout] bf16.  Adjoint of models/CustomLayers.py:170-171 wrt the weight; also used by the R1 double backward. */

@@ -16,7 +16,7 @@ from torch.autograd.function import once_differentiable
 from . import _geom
 from ._lib import lib, ptr, stream, code, count_launch, F32
 
-_state = {"dtype": torch.float32, "use_tc": True, "skip_param_grads": False}
+_state = {"dtype": torch.float32, "use_tc": True, "skip_param_grads": False, "fused_updown": True}
 
 
 class skip_param_grads:
@@ -1027,6 +1027,11 @@ def conv_layer(x, W, bias, kind, scale, bias_mul, act):
         from . import _tc
         N, H, Wd, _ = x.shape
         Hh, Wh = (2 * H, 2 * Wd) if kind != "down" else (H, Wd)
+        if _state["fused_updown"] and _tc.updown_supported(kind, N, Hh // 2, Wh // 2, ci, co):
+            # tap-merged tcgen05 kernel (16 tap-GEMMs per low-res pixel, no up-sampled / full-res intermediates)
+            if bias is None and not act:
+                return Conv.apply(x, W, kind, "fwd", scale)
+            return ConvBiasAct.apply(x, W, bias, kind, scale, bias_mul, act)
         if Hh <= 8 and Wh <= 8 and _tc.conv_and_wgrad_supported(N, 8, 16, ci, co):
             # tiny maps: same composition inside the padded 8x16 frame
             if kind == "down":

@@ -43,8 +43,58 @@ def conv_and_wgrad_supported(N, H, W, ci, co):
         and bool(lib.sg_wgrad3x3_tc_supported(N, H, W, ci, co))
 
 
+UP, DOWN = 0, 1
+
+
+def ud_mode(kind, direction):
+    """Geometry of the fused up/down kernel that evaluates (kind, direction)."""
+    if kind in ("up", "up_fused"):
+        return UP if direction == "fwd" else DOWN
+    return DOWN if direction == "fwd" else UP
+
+
+def ud_weight(W, kind, direction, scale):
+    """E[16][out][in] bf16 for sg_convud_tc from the host tap tables (models/_geom.py)."""
+    from . import _geom
+
+    def build():
+        co, ci = W.shape[0], W.shape[1]
+        t = _geom.tables(kind, 3, direction)
+        rows, cols = (co, ci) if direction == "fwd" else (ci, co)
+        E = torch.empty((16, rows, cols), dtype=torch.bfloat16, device=W.device)
+        coef = _ops._coef_dev(kind, 3, direction, W.device)
+        lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 16, ptr(coef), float(scale),
+                         1 - t["transpose"], stream())
+        count_launch()
+        return E
+    return _ops.cached_weight(W, ("tcud", kind, direction, float(scale)), build)
+
+
+def updown_supported(kind, N, Hlo, Wlo, ci, co):
+    """Fused up/down layer on the tensor cores: forward, dgrad and (via the 3x3 wgrad at high resolution) wgrad."""
+    m_f, m_d = ud_mode(kind, "fwd"), ud_mode(kind, "dgrad")
+    return bool(lib.sg_convud_tc_supported(m_f, N, Hlo, Wlo, ci, co)) and \
+        bool(lib.sg_convud_tc_supported(m_d, N, Hlo, Wlo, co, ci)) and \
+        bool(lib.sg_wgrad3x3_tc_supported(N, 2 * Hlo, 2 * Wlo, ci, co))
+
+
 def try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
-    if not _ops._state["use_tc"] or x.dtype != torch.bfloat16 or kind not in ("same", "same_flip"):
+    if not _ops._state["use_tc"] or x.dtype != torch.bfloat16:
+        return False
+    if kind in ("up", "up_fused", "down") and W.shape[2] == 3 and _ops._state.get("fused_updown", True):
+        co, ci = W.shape[0], W.shape[1]
+        cin, cout = (ci, co) if direction == "fwd" else (co, ci)
+        mode = ud_mode(kind, direction)
+        N, H, Wd, _ = x.shape
+        Hlo, Wlo = (H, Wd) if mode == UP else (H // 2, Wd // 2)
+        if not lib.sg_convud_tc_supported(mode, N, Hlo, Wlo, cin, cout):
+            return False
+        E = ud_weight(W, kind, direction, scale)
+        lib.sg_convud_tc(mode, ptr(x), ptr(E), ptr(y), ptr(bias), float(bias_mul), int(act), N, Hlo, Wlo, cin, cout,
+                         stream())
+        count_launch()
+        return True
+    if kind not in ("same", "same_flip"):
         return False
     co, ci, k, _ = W.shape
     if k != 3:
@@ -61,10 +111,29 @@ def try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
 
 def try_wgrad(xl, dyl, kind, scale, dW):
     """dW[co][ci][kh][kw] = scale * sum_p dy[p][co] x[p + (kh-1,kw-1)][ci] on the tensor cores."""
-    if not _ops._state["use_tc"] or xl.dtype != torch.bfloat16 or kind not in ("same", "same_flip"):
+    if not _ops._state["use_tc"] or xl.dtype != torch.bfloat16:
         return False
     co, ci, k, _ = dW.shape
     if k != 3:
+        return False
+    if kind in ("up", "up_fused", "down"):
+        # the up/down layers' weight gradient through the 3x3 kernel at the high resolution:
+        #   up:   dW = wgrad3x3(nearest_up2(x), dy)   (180-degree rotated taps for 'up_fused')
+        #   down: dW = wgrad3x3(x, nearest_up2(dy)/4)
+        N, H, Wd, _ = xl.shape
+        Hh, Wh = (2 * H, 2 * Wd) if kind != "down" else (H, Wd)
+        if not lib.sg_wgrad3x3_tc_supported(N, Hh, Wh, ci, co):
+            return False
+        if kind == "down":
+            gu = torch.empty((N, Hh, Wh, co), dtype=dyl.dtype, device=dyl.device)
+            lib.sg_up2_nhwc(ptr(dyl), ptr(gu), 0.25, BF16, N, Hh // 2, Wh // 2, co, stream())
+            count_launch()
+            return try_wgrad(xl, gu, "same", scale, dW)
+        xu = torch.empty((N, Hh, Wh, ci), dtype=xl.dtype, device=xl.device)
+        lib.sg_up2_nhwc(ptr(xl), ptr(xu), 1.0, BF16, N, H, Wd, ci, stream())
+        count_launch()
+        return try_wgrad(xu, dyl, "same" if kind == "up" else "same_flip", scale, dW)
+    if kind not in ("same", "same_flip"):
         return False
     N, H, Wd, _ = xl.shape
     if not lib.sg_wgrad3x3_tc_supported(N, H, Wd, ci, co):

@@ -109,3 +109,36 @@ def test_up_down_layers_on_tensor_cores(kind, ci, co, hw):
     got = torch.autograd.grad(y, [xd, Wd, bd], gy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16())
     assert rel(got[0].float().permute(0, 3, 1, 2), ref[0]) < 6e-2
     assert rel(got[1], ref[1]) < 6e-2 and rel(got[2], ref[2]) < 6e-2
+
+
+@pytest.mark.parametrize("kind", ["up", "up_fused", "down"])
+@pytest.mark.parametrize("direction", ["fwd", "dgrad"])
+@pytest.mark.parametrize("N,lo,ci,co", [(2, 16, 64, 64), (1, 32, 128, 64), (2, 16, 256, 128), (3, 64, 64, 128)])
+def test_fused_updown_kernel_matches_oracle(kind, direction, N, lo, ci, co):
+    """sg_convud_tc (tap-merged 4-phase 2x2 / 4x4-stride-2 tcgen05 kernels) vs torch on CPU, both directions."""
+    import test_gpu_ops as T
+    from models import _ops, _tc
+    from models._lib import lib
+    _ops.clear_weight_cache()
+    torch.manual_seed(4)
+    scale = O.he_scale(ci * 9, math.sqrt(2))
+    W = ((torch.randn(co, ci, 3, 3) * scale).bfloat16().float() / scale)
+    mode = _tc.ud_mode(kind, direction)
+    cin, cout = (ci, co) if direction == "fwd" else (co, ci)
+    if not lib.sg_convud_tc_supported(mode, N, lo, lo, cin, cout):
+        pytest.skip("shape not covered")
+    in_hw = lo if mode == _tc.UP else 2 * lo
+    xin = torch.randn(N, cin, in_hw, in_hw).bfloat16().float()
+    if direction == "fwd":
+        ref = T._ref_conv(kind, xin, W, scale)
+    else:
+        # adjoint of the forward map applied to xin (a tensor shaped like the forward OUTPUT)
+        fwd_in_hw = lo if kind != "down" else 2 * lo
+        probe = torch.zeros(N, ci, fwd_in_hw, fwd_in_hw, requires_grad=True)
+        (ref,) = torch.autograd.grad(T._ref_conv(kind, probe, W, scale), probe, xin)
+    xd = xin.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+    Wd = torch.nn.Parameter(W.to(DEV))
+    y = torch.empty((N, ref.shape[2], ref.shape[3], cout), dtype=torch.bfloat16, device=DEV)
+    assert _tc.try_conv(xd, Wd, kind, direction, scale, None, 1.0, False, y)      # the fused tensor-core path
+    torch.cuda.synchronize()
+    assert rel(y.float().permute(0, 3, 1, 2), ref) < 1e-2

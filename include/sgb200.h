@@ -81,6 +81,14 @@ int sg_wgrad3x3_tc_supported(int N, int H, int W, int Cin, int Cout);
 int sg_wgrad3x3_tc_splits(int N, int H, int W, int Cin, int Cout);
 int sg_wgrad3x3_tc(const void* x, const void* dy, float* part, int N, int H, int W, int Cin, int Cout, void* stream);
 
+/* tcgen05/TMA weight gradient of the up/down layers in the tap-merged form (csrc/sg_wgradud_tc.cu): part
+ * [S][16][Cout][Cin] float32 (tap order of the layer's table), reduced onto the 3x3 parameter by sg_wprep_bwd with the
+ * coefficient table of models/_geom.py (transpose=1).  H, W = low-resolution grid. */
+int sg_wgradud_tc_supported(int mode, int N, int H, int W, int Cin, int Cout);
+int sg_wgradud_tc_splits(int mode, int N, int H, int W, int Cin, int Cout);
+int sg_wgradud_tc(int mode, const void* x, const void* dy, float* part, int N, int H, int W, int Cin, int Cout,
+                  void* stream);
+
 /* ---- bandwidth-bound feature-map kernels ------------------------------------------------------------------------ */
 /* BlurLayer.forward, CustomLayers.py:266-276 (+ the `x + bias` of :178-179 when bias != NULL). Self-adjoint. */
 int sg_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W, int C,

@@ -122,6 +122,16 @@ def try_wgrad(xl, dyl, kind, scale, dW):
         #   down: dW = wgrad3x3(x, nearest_up2(dy)/4)
         N, H, Wd, _ = xl.shape
         Hh, Wh = (2 * H, 2 * Wd) if kind != "down" else (H, Wd)
+        mode = DOWN if kind == "down" else UP
+        if _ops._state.get("fused_updown", True) and lib.sg_wgradud_tc_supported(mode, N, Hh // 2, Wh // 2, ci, co):
+            # tap-merged kernel: 16 tap accumulators, stride-2 TMA gathers, then the table's adjoint onto the 3x3 weight
+            S = lib.sg_wgradud_tc_splits(mode, N, Hh // 2, Wh // 2, ci, co)
+            part = torch.empty((S, 16, co, ci), dtype=torch.float32, device=xl.device)
+            lib.sg_wgradud_tc(mode, ptr(xl), ptr(dyl), ptr(part), N, Hh // 2, Wh // 2, ci, co, stream())
+            coef = _ops._coef_dev(kind, 3, "fwd", xl.device)
+            lib.sg_wprep_bwd(ptr(part), S, ptr(dW), co, ci, 9, 16, ptr(coef), float(scale), 1, 0, stream())
+            count_launch(2)
+            return True
         if not lib.sg_wgrad3x3_tc_supported(N, Hh, Wh, ci, co):
             return False
         if kind == "down":

@@ -16,7 +16,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

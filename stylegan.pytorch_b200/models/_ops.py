@@ -7,14 +7,13 @@ backward pass without PyTorch having to see inside a kernel.  Generator-only Fun
 
 PyTorch is plumbing here: it owns memory, streams and the autograd tape; all arithmetic is in the kernels."""
 import ctypes
-import math
 
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _geom
-from ._lib import lib, ptr, stream, code, count_launch, F32
+from ._lib import lib, ptr, stream, code, count_launch
 
 _state = {"dtype": torch.float32, "use_tc": True, "skip_param_grads": False, "fused_updown": True}
 

@@ -4,8 +4,6 @@
 layout of the reference's GAN_*_OPTIM_*.pth files (reference GAN.py:529-533, 816-817): per-parameter ``step``,
 ``exp_avg``, ``exp_avg_sq`` in ``module.parameters()`` order.  ``step()`` is one kernel launch over all tensors
 (plus a one-block step-counter bump) instead of hundreds of per-tensor ops."""
-import ctypes
-
 import torch
 
 from . import _ops

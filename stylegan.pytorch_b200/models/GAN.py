@@ -376,9 +376,8 @@ class StyleGAN:
                 loss = self.loss.dis_loss(real_samples, fake_samples, labels, depth, alpha)
             self.dis_optim.zero_grad()
             loss.backward()
-            if self.ddp is not None:
-                self.ddp.allreduce_grads(self.dis_optim)
-            self.dis_optim.step()
+            gscale = self.ddp.allreduce_grads(self.dis_optim) if self.ddp is not None else 1.0
+            self.dis_optim.step(grad_scale=gscale)
             loss_val += loss.item()
         return loss_val / self.d_repeats
 
@@ -406,14 +405,13 @@ class StyleGAN:
         # only generator parameters need gradients here (the reference also accumulates unused D gradients)
         g_params = [p for p in self.gen.parameters() if p.requires_grad]
         loss.backward(inputs=g_params)
-        if self.ddp is not None:
-            self.ddp.allreduce_grads(self.gen_optim)
+        gscale = self.ddp.allreduce_grads(self.gen_optim) if self.ddp is not None else 1.0
         # clip_grad_norm_(max_norm=10) + Adam + EMA in one multi-tensor pass
         shadow = dict(self.gen_shadow.named_parameters()) if self.use_ema else None
         ema_map = None
         if shadow is not None:
             ema_map = {p: shadow[n] for n, p in self.gen.named_parameters()}
-        self.gen_optim.step(max_norm=10., ema_map=ema_map, ema_decay=self.ema_decay)
+        self.gen_optim.step(max_norm=10., ema_map=ema_map, ema_decay=self.ema_decay, grad_scale=gscale)
         return loss.item()
 
     @staticmethod

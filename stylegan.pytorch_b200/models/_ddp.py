@@ -60,15 +60,16 @@ class DataParallelContext:
         return flats, works, placement
 
     def allreduce_grads(self, optim):
-        """Average the gradients of `optim`'s parameters across ranks.  The 1/world scale is applied in place here
-        so that every downstream consumer (clip norm, Adam) sees averaged gradients."""
+        """SUM-reduce the gradients of `optim`'s parameters across ranks into flat buckets and re-point each `.grad`
+        into its bucket.  Returns the scale (1/world) that turns the sums into averages; the fused Adam kernel applies
+        it (to the clip norm as well), so no extra pass over the gradients is made."""
         params = [p for g in optim.param_groups for p in g["params"] if p.grad is not None]
         if not params:
-            return
+            return 1.0
         grads = [p.grad for p in params]
         flats, works, placement = self.reduce_buckets(grads)
-        for b, (flat, w) in enumerate(zip(flats, works)):
+        for w in works:
             w.wait()
-            flat.mul_(1.0 / self.world)
         for p, (b, off) in zip(params, placement):
             p.grad = flats[b][off:off + p.numel()].view_as(p)
+        return 1.0 / self.world

@@ -41,7 +41,8 @@ def _worker(rank, world, port, q):
             g_local.append(p.grad.clone())
         params[5].grad = None                        # a parameter unused at this depth on every rank
         opt = torch.optim.SGD(params, lr=0.1)
-        ctx.allreduce_grads(opt)
+        scale = ctx.allreduce_grads(opt)
+        assert abs(scale - 1.0 / world) < 1e-12
         gathered = []
         for i, g in enumerate(g_local):
             if i == 5:
@@ -49,7 +50,7 @@ def _worker(rank, world, port, q):
             buf = [torch.zeros_like(g) for _ in range(world)]
             dist.all_gather(buf, g)
             gathered.append(sum(buf) / world)
-        got = [p.grad for i, p in enumerate(params) if i != 5]
+        got = [p.grad * scale for i, p in enumerate(params) if i != 5]    # sums; the Adam kernel applies `scale`
         ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(got, gathered)) and params[5].grad is None
         q.put((rank, ok))
     finally:

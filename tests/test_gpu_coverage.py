@@ -181,3 +181,51 @@ def test_bf16_training_is_stable_and_learns():
     assert 0 < float((s1 - s0).abs().max()) < float((w1 - w0).abs().max())
     out = sg.gen_shadow(torch.randn(4, 64, device=DEV), depth, 1.0)
     assert out.shape == (4, 3, 32, 32) and bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-3), ("bf16", 8e-2)])
+def test_full_width_step_vs_oracle(prec, tol):
+    """One G+D step at the reference's REAL channel widths (512/512/512/512/256 at 4..64 px, batch 4, depth 4,
+    alpha 0.5, logistic + R1, EMA) against the CPU oracle: losses and a few updated parameters."""
+    import models
+    from models.GAN import StyleGAN
+    from models.CustomLayers import NoiseLayer
+    from models import _ops
+    arch = O.Arch(64)
+    gen = torch.Generator().manual_seed(11)
+    g_sd, d_sd = O.init_generator(arch, gen), O.init_discriminator(arch, gen)
+    for k in g_sd:
+        if k.endswith("noise.weight"):
+            g_sd[k] = 0.5 * torch.randn(g_sd[k].shape, generator=gen)
+    B, depth, alpha = 4, 4, 0.5
+    noises = [torch.randn(s, generator=gen) for s in O.noise_shapes(arch, B, depth)]
+    z = torch.randn(B, 512, generator=gen)
+    img = torch.randn(B, 3, 64, 64, generator=gen)
+    torch.manual_seed(5); random.seed(5)
+    st = O.TrainState(arch, g_sd, d_sd)
+    mix_d = O.draw_mixing(arch, z.shape, depth)
+    mix_g = O.draw_mixing(arch, z.shape, depth)
+    dl_o, gl_o = O.train_step(st, img, z, depth, alpha, mix_d, mix_g, noises, noises)
+
+    models.set_precision(prec)
+    opt = dict(learning_rate=0.003, beta_1=0, beta_2=0.99, eps=1e-8)
+    sg = StyleGAN("linear", 64, 3, 512, dict(latent_size=512, mapping_layers=4, blur_filter=[1, 2, 1],
+                                             truncation_psi=0.7, truncation_cutoff=8),
+                  dict(use_wscale=True, blur_filter=[1, 2, 1]), opt, dict(opt), loss="logistic", use_ema=True,
+                  device=torch.device(DEV))
+    sg.gen.load_state_dict(g_sd); sg.dis.load_state_dict(d_sd); sg.gen_shadow.load_state_dict(g_sd)
+    _ops.clear_weight_cache()
+    for m, n in zip([m for m in sg.gen.g_synthesis.modules() if isinstance(m, NoiseLayer)], noises):
+        m.noise = n.to(DEV)
+    torch.manual_seed(5); random.seed(5)
+    dl = sg.optimize_discriminator(z.to(DEV), img.to(DEV), depth, alpha)
+    gl = sg.optimize_generator(z.to(DEV), img.to(DEV), depth, alpha)
+    assert abs(dl - dl_o) <= tol * abs(dl_o), (prec, dl, dl_o)
+    assert abs(gl - gl_o) <= tol * abs(gl_o) + (0.02 if prec == "bf16" else 0.0), (prec, gl, gl_o)
+    if prec == "fp32":
+        # after one Adam step with beta1 = 0 every touched parameter moved by ~lr*sign(g): compare the directions
+        for k in ("final_block.dense1.weight", "blocks.2.conv0.bias", "from_rgb.1.weight"):
+            mine = sg.dis.state_dict()[k].cpu() - d_sd[k]
+            ref = st.d[k] - d_sd[k]
+            agree = float(((mine * ref) > 0).float().mean())
+            assert agree > 0.97, (k, agree)

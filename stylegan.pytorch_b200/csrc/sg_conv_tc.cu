@@ -234,7 +234,9 @@ static int pick_bn(int Cin, int Cout) {
 
 SG_EXPORT int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout) {
   if (N < 1 || H % tc::TH != 0 || W % tc::TW != 0) return 0;
-  if (Cin % tc::BK != 0) return 0;
+  // Cin need not be a multiple of 64: the TMA boxes are 64 channels wide and the part beyond the tensor is
+  // zero-filled in shared memory (only the 16-byte global stride rule applies)
+  if (Cin < 16 || Cin % 8 != 0) return 0;
   if (tc::pick_bn(Cin, Cout) == 0) return 0;
   return 1;
 }
@@ -264,7 +266,7 @@ SG_EXPORT int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.BN = BN;
   p.tiles_h = H / TH; p.tiles_w = W / TW; p.tiles_n = Cout / BN;
   p.num_spatial = N * p.tiles_h * p.tiles_w;
-  p.kchunks = Cin / BK;
+  p.kchunks = (Cin + BK - 1) / BK;
   p.resident = resident_ok(Cin, Cout) ? 1 : 0;
   p.w_bytes = p.resident ? 9 * p.kchunks * BN * BK * 2 : 0;
   p.stage_bytes = p.resident ? A_BYTES : A_BYTES + 3 * BN * BK * 2;

@@ -257,7 +257,7 @@ static bool encode_nhwc_stride2(CUtensorMap* map, const void* ptr, int N, int H,
 SG_EXPORT int sg_convud_tc_supported(int mode, int N, int H, int W, int Cin, int Cout) {
   if (mode != 0 && mode != 1) return 0;
   if (N < 1 || H % ud::TH != 0 || W % ud::TW != 0) return 0;
-  if (Cin % ud::BK != 0) return 0;
+  if (Cin < 16 || Cin % 8 != 0) return 0;      // 64-channel TMA boxes, zero-filled beyond Cin
   if (ud::pick_bn(Cout) == 0) return 0;
   return 1;
 }
@@ -295,7 +295,7 @@ SG_EXPORT int sg_convud_tc(int mode, const void* x, const void* E, void* y, cons
   p.num_spatial = N * p.tiles_h * p.tiles_w;
   p.nphase = (mode == MODE_UP) ? 4 : 1;
   p.nbox = (mode == MODE_UP) ? 2 : 8;
-  p.kchunks = Cin / BK;
+  p.kchunks = (Cin + BK - 1) / BK;
   p.stage_bytes = A_BYTES + 2 * BN * BK * 2;
   int stages = (214 * 1024) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;

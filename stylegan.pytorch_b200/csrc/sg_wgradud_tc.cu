@@ -163,7 +163,7 @@ wgradud_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
-          if (active) {
+          if (active && co < p.Cout && nb * p.BN + c0 < p.Cin) {
             float4* d4 = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -185,9 +185,12 @@ wgradud_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   }
 }
 
+// Channel block of the GEMM's M / N dimension.  Channel counts below 64 use a 64-wide block: the TMA box reads past
+// the tensor's channel extent, which arrives as zeros, and the epilogue writes only the real rows / columns.
 static int pick_block(int C) {
   if (C % 128 == 0) return 128;
   if (C == 64) return 64;
+  if (C < 64 && C % 16 == 0) return 64;
   return 0;
 }
 
@@ -218,7 +221,7 @@ SG_EXPORT int sg_wgradud_tc_supported(int mode, int N, int H, int W, int Cin, in
 SG_EXPORT int sg_wgradud_tc_splits(int mode, int N, int H, int W, int Cin, int Cout) {
   if (!sg_wgradud_tc_supported(mode, N, H, W, Cin, Cout)) return 0;
   int total = N * (H / wgud::TH) * (W / wgud::TW);
-  int units = 4 * (Cout / wgud::pick_block(Cout)) * (Cin / wgud::pick_block(Cin));
+  int units = 4 * ((Cout + wgud::pick_block(Cout) - 1) / wgud::pick_block(Cout)) * ((Cin + wgud::pick_block(Cin) - 1) / wgud::pick_block(Cin));
   int S = (148 + units - 1) / units;
   if (S > total) S = total;
   if (S < 1) S = 1;
@@ -244,7 +247,7 @@ SG_EXPORT int sg_wgradud_tc(int mode, const void* x, const void* dy, float* part
   p.mode = mode; p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.BM = pick_block(Cout); p.BN = pick_block(Cin);
   p.tiles_h = H / TH; p.tiles_w = W / TW; p.total_tiles = N * p.tiles_h * p.tiles_w;
-  p.MB = Cout / p.BM; p.NB = Cin / p.BN;
+  p.MB = (Cout + p.BM - 1) / p.BM; p.NB = (Cin + p.BN - 1) / p.BN;
   p.S = sg_wgradud_tc_splits(mode, N, H, W, Cin, Cout);
   p.stage_bytes = (p.BM / 64) * DY_BLOCK_BYTES + (p.BN / 64) * X_BLOCK_BYTES;
   int stages = (214 * 1024) / p.stage_bytes;

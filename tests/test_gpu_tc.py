@@ -58,7 +58,8 @@ def test_conv3x3_tc_matches_oracle(N, H, W, ci, co, direction):
 def test_unsupported_shapes_fall_back_to_generic_kernel():
     from models._lib import lib
     assert lib.sg_conv3x3_tc_supported(2, 4, 4, 64, 64) == 0      # below the 8x16 tile
-    assert lib.sg_conv3x3_tc_supported(2, 16, 16, 32, 64) == 0    # Cin not a multiple of 64
+    assert lib.sg_conv3x3_tc_supported(2, 16, 16, 32, 64) == 1    # Cin < 64: TMA zero-fills the channel padding
+    assert lib.sg_conv3x3_tc_supported(2, 16, 16, 12, 64) == 0    # global stride not a multiple of 16 bytes
     assert lib.sg_conv3x3_tc_supported(2, 16, 16, 64, 513) == 0
 
 
@@ -85,7 +86,10 @@ def test_wgrad3x3_tc_matches_oracle(N, H, W, ci, co):
 
 @pytest.mark.parametrize("kind,ci,co,hw", [("up", 128, 64, 16), ("up_fused", 128, 64, 64), ("down", 64, 128, 32),
                                             ("down", 64, 128, 128), ("same", 128, 128, 4), ("same", 64, 128, 8),
-                                            ("up", 128, 128, 4), ("down", 128, 64, 8)])
+                                            ("up", 128, 128, 4), ("down", 128, 64, 8),
+                                            # channel counts below 64 (the 512x512 / 1024x1024 layers): TMA zero-fills
+                                            ("same", 32, 32, 32), ("same", 16, 16, 64), ("up_fused", 64, 32, 64),
+                                            ("up_fused", 32, 16, 64), ("down", 16, 32, 128), ("down", 32, 64, 64)])
 def test_up_down_layers_on_tensor_cores(kind, ci, co, hw):
     """bf16 up/down EqualizedConv2d layers (nearest-up -> tc conv, tc conv -> box pool) vs the oracle, fwd + grads."""
     from models import _ops

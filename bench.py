@@ -272,16 +272,20 @@ def main():
             dist.barrier()
         return float(ms)
 
-    for i in range(args.warmup):
-        step_resident(i)
+    import gc
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                    # spawned before the warm-up so that its start-up cost is not in the timing
+    for i in range(args.warmup):
+        step_resident(i)
+    gc.collect()
+    gc.disable()                           # no collector pauses inside the timed regions
     l0 = _lib.launches()
     ms = timed(step_resident, args.steps)
     launches = _lib.launches() - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps)
+    gc.enable()
 
     if rank == 0:
         pk, how = peaks()

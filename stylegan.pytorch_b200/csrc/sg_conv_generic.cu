@@ -243,20 +243,26 @@ __global__ void __launch_bounds__(NT) wgrad_generic_kernel(const T* __restrict__
 template <class T>
 __global__ void wprep_fwd_kernel(const float* __restrict__ W, T* __restrict__ E, int Cout, int Cin, int KK,
                                  int npt, const float* __restrict__ coef, float scale, int transpose) {
+  // one thread per (a,b): the KK parameter taps are read once and every effective tap is written (coalesced over b)
+  extern __shared__ float s_coef[];                 // [npt][KK]
+  for (int i = threadIdx.x; i < npt * KK; i += blockDim.x) s_coef[i] = coef[i];
+  __syncthreads();
   const int A = transpose ? Cout : Cin, B = transpose ? Cin : Cout;
-  const long long total = (long long)npt * A * B;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+  const long long AB = (long long)A * B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < AB;
        i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i % B);
-    long long r = i / B;
-    int a = (int)(r % A);
-    int pt = (int)(r / A);
+    int a = (int)(i / B);
     int co = transpose ? a : b, ci = transpose ? b : a;
     const float* w = W + ((size_t)co * Cin + ci) * KK;
-    const float* c = coef + (size_t)pt * KK;
-    float s = 0.f;
-    for (int j = 0; j < KK; ++j) s = fmaf(c[j], w[j], s);
-    E[i] = sg_from_f<T>(s * scale);
+    float wv[16];
+    for (int j = 0; j < KK; ++j) wv[j] = w[j] * scale;
+    for (int pt = 0; pt < npt; ++pt) {
+      const float* c = s_coef + pt * KK;
+      float s = 0.f;
+      for (int j = 0; j < KK; ++j) s = fmaf(c[j], wv[j], s);
+      E[(size_t)pt * AB + i] = sg_from_f<T>(s);
+    }
   }
 }
 
@@ -336,10 +342,11 @@ SG_EXPORT int sg_wgrad_splits(const SgConvGeom* g) {
 SG_EXPORT int sg_wprep_fwd(const float* W, void* E, int dtype, int Cout, int Cin, int KK, int npt, const float* coef,
                            float scale, int transpose, void* stream) {
   SG_REQUIRE(KK >= 1 && KK <= 16 && npt >= 1, "sg_wprep_fwd: bad sizes");
-  long long total = (long long)npt * Cout * Cin;
+  SG_REQUIRE(npt <= 64, "sg_wprep_fwd: too many effective taps");
+  long long total = (long long)Cout * Cin;
   cudaStream_t st = (cudaStream_t)stream;
   SG_DISPATCH(dtype, {
-    wprep_fwd_kernel<T><<<sg_grid_1d(total, 256), 256, 0, st>>>(W, (T*)E, Cout, Cin, KK, npt, coef, scale, transpose);
+    wprep_fwd_kernel<T><<<sg_grid_1d(total, 128), 128, (size_t)npt * KK * sizeof(float), st>>>(W, (T*)E, Cout, Cin, KK, npt, coef, scale, transpose);
   });
   return sg_check_launch("sg_wprep_fwd");
 }

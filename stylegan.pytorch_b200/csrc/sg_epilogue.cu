@@ -121,36 +121,51 @@ __global__ void __launch_bounds__(256) epi_reduce_vec_kernel(const T* __restrict
         if (blockIdx.x == 0 && pr == 0) sums[((size_t)n * C + cv * V::N + k) * 3 + 2] = (double)a0[k];
       }
     }
-    for (int p = p0 + pr; p < p1; p += PR) {
-      const size_t idx = (base + p) * C + cv * V::N;
-      if (MODE == 0) {
-        V vi, vo;
-        vi.load(in0 + idx);
-        const float nz = noise ? noise[base + p] : 0.f;
+    constexpr int U = 4;                          // pixels in flight per thread
+    for (int pb = p0 + pr; pb < p1; pb += U * PR) {
+      V va[U], vb[U];
+      float nz[U];
+      bool ok[U];
 #pragma unroll
-        for (int k = 0; k < V::N; ++k) {
-          float v = vi.get(k) + b[k];
-          if (noise) v = fmaf(nw[k], nz, v);
-          if (act) v = sg_lrelu(v);
-          vo.set(k, v);
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * PR;
+        ok[u] = p < p1;
+        nz[u] = 0.f;
+        if (ok[u]) {
+          const size_t idx = (base + p) * C + cv * V::N;
+          va[u].load(in0 + idx);
+          if (MODE == 0) { if (noise) nz[u] = noise[base + p]; }
+          else vb[u].load(in1 + idx);
         }
-        vo.store(zout + idx);
+      }
 #pragma unroll
-        for (int k = 0; k < V::N; ++k) {
-          float zr = vo.get(k) - a0[k];
-          s0[k] += zr;
-          s1[k] = fmaf(zr, zr, s1[k]);
-        }
-      } else {
-        V vg, vz;
-        vg.load(in0 + idx);
-        vz.load(in1 + idx);
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const size_t idx = (base + pb + u * PR) * C + cv * V::N;
+        if (MODE == 0) {
+          V vo;
 #pragma unroll
-        for (int k = 0; k < V::N; ++k) {
-          float g = vg.get(k);
-          float xh = (vz.get(k) - a0[k]) * a1[k];
-          s0[k] += g;
-          s1[k] = fmaf(g, xh, s1[k]);
+          for (int k = 0; k < V::N; ++k) {
+            float v = va[u].get(k) + b[k];
+            if (noise) v = fmaf(nw[k], nz[u], v);
+            if (act) v = sg_lrelu(v);
+            vo.set(k, v);
+          }
+          vo.store(zout + idx);
+#pragma unroll
+          for (int k = 0; k < V::N; ++k) {
+            float zr = vo.get(k) - a0[k];
+            s0[k] += zr;
+            s1[k] = fmaf(zr, zr, s1[k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < V::N; ++k) {
+            float g = va[u].get(k);
+            float xh = (vb[u].get(k) - a0[k]) * a1[k];
+            s0[k] += g;
+            s1[k] = fmaf(g, xh, s1[k]);
+          }
         }
       }
     }

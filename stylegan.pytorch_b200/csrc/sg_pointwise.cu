@@ -216,20 +216,34 @@ __global__ void __launch_bounds__(256) channel_sum_vec_kernel(const T* __restric
 #pragma unroll
     for (int k = 0; k < V::N; ++k) acc[j][k] = 0.f;
   if (pr < PR) {
-    for (long long p = p0 + pr; p < p1; p += PR) {
-      V v;
-      v.load(x + (size_t)p * C + cv * V::N);
-      long long n = p / HW;
-      int hw = (int)(p - n * HW);
-      float w[CS_ROWS];
+    constexpr int U = 4;                          // pixels in flight per thread
+    for (long long pb = p0 + pr; pb < p1; pb += (long long)U * PR) {
+      V v[U];
+      float w[U][CS_ROWS];
 #pragma unroll
-      for (int j = 0; j < CS_ROWS; ++j) w[j] = (j < J) ? wt[((size_t)n * J + j) * HW + hw] : ((ones && j == J) ? 1.f : 0.f);
+      for (int u = 0; u < U; ++u) {
+        const long long p = pb + (long long)u * PR;
+        if (p < p1) {
+          v[u].load(x + (size_t)p * C + cv * V::N);
+          long long n = p / HW;
+          int hw = (int)(p - n * HW);
 #pragma unroll
-      for (int k = 0; k < V::N; ++k) {
-        float f = v.get(k);
+          for (int j = 0; j < CS_ROWS; ++j)
+            w[u][j] = (j < J) ? wt[((size_t)n * J + j) * HW + hw] : ((ones && j == J) ? 1.f : 0.f);
+        } else {
+          v[u].zero();
 #pragma unroll
-        for (int j = 0; j < CS_ROWS; ++j) acc[j][k] = fmaf(w[j], f, acc[j][k]);
+          for (int j = 0; j < CS_ROWS; ++j) w[u][j] = 0.f;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) {
+          float f = v[u].get(k);
+#pragma unroll
+          for (int j = 0; j < CS_ROWS; ++j) acc[j][k] = fmaf(w[u][j], f, acc[j][k]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < CS_ROWS; ++j)
@@ -330,11 +344,27 @@ __global__ void rgb_in_dgrad_kernel(const T* __restrict__ g, const float* __rest
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int CV = C / V::N;
+  // weights of this lane's first channel vector in registers (the only one when CV <= G, the common case)
+  float wreg[V::N][4];
+#pragma unroll
+  for (int e = 0; e < V::N; ++e)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wreg[e][k] = (l < CV && k < K) ? Wt[(l * V::N + e) * K + k] : 0.f;
   for (long long p0 = warp * per_warp; p0 < P; p0 += nwarps * per_warp) {
     const long long p = p0 + sub;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (p < P) {
-      for (int cv = l; cv < CV; cv += G) {
+      if (l < CV) {
+        V v;
+        v.load(g + (size_t)p * C + l * V::N);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) {
+          float f = v.get(e);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[k] = fmaf(f, wreg[e][k], acc[k]);
+        }
+      }
+      for (int cv = l + G; cv < CV; cv += G) {
         V v;
         v.load(g + (size_t)p * C + cv * V::N);
 #pragma unroll

@@ -15,6 +15,8 @@ constexpr int LF_IC = 256;    // input chunk staged in shared memory
 constexpr int LF_BMAX = 32;   // batch rows per pass
 // block = 8 warps; warp w owns output o = blockIdx.x*8 + w; x is staged [rows][256] in shared memory so that it is
 // read from L2 once per block instead of once per warp.
+// gridDim.y > 1 splits the input dimension: each slice atomically adds its partial products into y (pre-zeroed) and
+// linear_finish_kernel applies scale / bias / activation afterwards.
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, long long ldx,
                                                          const float* __restrict__ W, const float* __restrict__ bias,
                                                          float scale, float bias_mul, int act, float* __restrict__ y,
@@ -23,12 +25,16 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * LF_OB + warp;
   const float* w = W + (size_t)(o < O ? o : 0) * I;
+  const bool split = gridDim.y > 1;
+  const int i_per = ((I + gridDim.y - 1) / gridDim.y + LF_IC - 1) / LF_IC * LF_IC;
+  const int i_begin = blockIdx.y * i_per;
+  const int i_end = (i_begin + i_per < I) ? (i_begin + i_per) : I;
   for (int b0 = 0; b0 < B; b0 += LF_BMAX) {
     const int nb = (B - b0 < LF_BMAX) ? (B - b0) : LF_BMAX;
     float acc[LF_BMAX];
 #pragma unroll
     for (int j = 0; j < LF_BMAX; ++j) acc[j] = 0.f;
-    for (int i0 = 0; i0 < I; i0 += LF_IC) {
+    for (int i0 = i_begin; i0 < i_end; i0 += LF_IC) {
       __syncthreads();
       for (int t = threadIdx.x; t < nb * LF_IC; t += blockDim.x) {
         int r = t / LF_IC, c = t % LF_IC;
@@ -52,13 +58,25 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
         if (j < nb) {
           float s = sg_warp_sum(acc[j]);
           if (lane == 0) {
-            s = s * scale + (bias ? bias[o] * bias_mul : 0.f);
-            y[(size_t)(b0 + j) * O + o] = act ? sg_lrelu(s) : s;
+            if (split) {
+              atomicAdd(&y[(size_t)(b0 + j) * O + o], s);
+            } else {
+              s = s * scale + (bias ? bias[o] * bias_mul : 0.f);
+              y[(size_t)(b0 + j) * O + o] = act ? sg_lrelu(s) : s;
+            }
           }
         }
       }
     }
   }
+}
+
+__global__ void linear_finish_kernel(float* __restrict__ y, const float* __restrict__ bias, float scale,
+                                     float bias_mul, int act, int B, int O) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * O) return;
+  float s = y[i] * scale + (bias ? bias[i % O] * bias_mul : 0.f);
+  y[i] = act ? sg_lrelu(s) : s;
 }
 
 // gx[b][i] = scale * sum_o gy[b][o] * W[o][i].  grid (I/128, O splits): a thread owns column i for up to 32 batch
@@ -329,7 +347,15 @@ __global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float*
 
 SG_EXPORT int sg_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale,
                             float bias_mul, int act, float* y, int B, int I, int O, void* stream) {
-  linear_fwd_kernel<<<sg_cdiv(O, LF_OB), 256, 0, (cudaStream_t)stream>>>(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O);
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits = 1;
+  if (I >= 2048) {                                  // wide input (discriminator dense0): split I to fill the GPU
+    splits = I / 1024;
+    if (splits > 16) splits = 16;
+  }
+  if (splits > 1) cudaMemsetAsync(y, 0, (size_t)B * O * sizeof(float), st);
+  linear_fwd_kernel<<<dim3(sg_cdiv(O, LF_OB), splits), 256, 0, st>>>(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O);
+  if (splits > 1) linear_finish_kernel<<<sg_cdiv((long long)B * O, 256), 256, 0, st>>>(y, bias, scale, bias_mul, act, B, O);
   return sg_check_launch("sg_linear_fwd");
 }
 

@@ -50,6 +50,11 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            # nvidia-smi's own start-up (NVML init) briefly stalls kernel launches: wait for its first sample so
+            # that cost lands before the warm-up, not inside the timed region
+            t0 = time.time()
+            while time.time() - t0 < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

@@ -221,14 +221,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-// Resident-weight mode: the 9*Cin*BN bf16 weights of one N block fit beside >= 3 activation stages.
-static bool resident_ok(int Cin, int Cout) { return Cin <= 128 && (Cout % 64 == 0 || (Cout < 64 && Cout % 16 == 0)); }
+// N block: 128 whenever Cout allows it (a 128x128x16 MMA reads 8 KB of operands in its 64 tensor cycles, while N = 64
+// is bound by shared-memory operand bandwidth), otherwise the whole Cout (16..112).
 static int pick_bn(int Cin, int Cout) {
-  if (resident_ok(Cin, Cout)) return Cout < 64 ? Cout : 64;
+  (void)Cin;
   if (Cout % 128 == 0) return 128;
   if (Cout <= 128 && Cout % 16 == 0) return Cout;
   return 0;
 }
+// Resident-weight mode: the 9 * ceil(Cin/64) weight tiles of one N block fit beside >= 3 activation stages.
+static bool resident_ok(int Cin, int BN) { return 9 * ((Cin + BK - 1) / BK) * BN * BK * 2 <= 150 * 1024; }
 
 }  // namespace tc
 
@@ -267,7 +269,7 @@ SG_EXPORT int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float
   p.tiles_h = H / TH; p.tiles_w = W / TW; p.tiles_n = Cout / BN;
   p.num_spatial = N * p.tiles_h * p.tiles_w;
   p.kchunks = (Cin + BK - 1) / BK;
-  p.resident = resident_ok(Cin, Cout) ? 1 : 0;
+  p.resident = resident_ok(Cin, BN) ? 1 : 0;
   p.w_bytes = p.resident ? 9 * p.kchunks * BN * BK * 2 : 0;
   p.stage_bytes = p.resident ? A_BYTES : A_BYTES + 3 * BN * BK * 2;
   int stages = (216 * 1024 - p.w_bytes) / p.stage_bytes;

@@ -186,9 +186,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
           packed[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-        d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        st_global_256(dst + c0, packed);
       };
       for (int c0 = 0; c0 < p.BN; c0 += 64) {
         // up to four 16-column TMEM loads in flight, one wait

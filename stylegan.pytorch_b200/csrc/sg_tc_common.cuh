@@ -114,6 +114,13 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// One 32-byte global store (sm_100 STG.256): a full L2 sector per thread instead of two half-sector writes.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // split form: issue several loads, then one wait
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

@@ -267,27 +267,89 @@ __global__ void wprep_fwd_kernel(const float* __restrict__ W, T* __restrict__ E,
 }
 
 // dW[co][ci][j] (+)= scale * sum_{pt} coef[pt][j] * sum_s partial[s][pt][a][b]
-__global__ void wprep_bwd_kernel(const float* __restrict__ partial, int nsplit, float* __restrict__ dW, int Cout,
-                                 int Cin, int KK, int npt, const float* __restrict__ coef, float scale,
-                                 int transpose, int accumulate) {
+constexpr int WB_AB = 32;    // (a,b) weight positions per CTA
+constexpr int WB_PT = 16;    // tap slots per CTA (npt <= 16)
+__global__ void __launch_bounds__(WB_AB * WB_PT)
+wprep_bwd_kernel(const float* __restrict__ partial, int nsplit, float* __restrict__ dW, int Cout, int Cin, int KK,
+                 int npt, const float* __restrict__ coef, float scale, int transpose, int accumulate) {
+  // phase 1: thread (pt, ab) sums its element over the pixel splits (4 independent chains);
+  // phase 2: thread (ab, j) combines the npt tap sums with the transposed coefficient table and writes dW.
+  // (One thread per (a,b) walking all npt*nsplit partials serially cost 50-70 us on the 64/128-channel layers.)
+  __shared__ float s_sum[WB_PT][WB_AB + 1];
+  __shared__ float s_coef[WB_PT * 16];
   const int A = transpose ? Cout : Cin, B = transpose ? Cin : Cout;
   const long long total = (long long)A * B;
-  const size_t split_stride = (size_t)npt * A * B;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int b = (int)(i % B), a = (int)(i / B);
-    int co = transpose ? a : b, ci = transpose ? b : a;
-    float out[16];
-    for (int j = 0; j < KK; ++j) out[j] = 0.f;
-    for (int pt = 0; pt < npt; ++pt) {
-      float s = 0.f;
-      const float* p = partial + (size_t)pt * A * B + i;
-      for (int sp = 0; sp < nsplit; ++sp) s += p[(size_t)sp * split_stride];
-      const float* c = coef + (size_t)pt * KK;
-      for (int j = 0; j < KK; ++j) out[j] = fmaf(c[j], s, out[j]);
+  const size_t plane = (size_t)A * B;
+  const size_t split_stride = (size_t)npt * plane;
+  for (int i = threadIdx.x; i < npt * KK; i += blockDim.x) s_coef[i] = coef[i];
+  const int ab_l = threadIdx.x % WB_AB, pt = threadIdx.x / WB_AB;
+  const long long i0 = (long long)blockIdx.x * WB_AB;
+  if (pt < npt && i0 + ab_l < total) {
+    const float* p = partial + (size_t)pt * plane + (size_t)(i0 + ab_l);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int sp = 0;
+    for (; sp + 4 <= nsplit; sp += 4) {
+      s0 += p[(size_t)sp * split_stride];
+      s1 += p[(size_t)(sp + 1) * split_stride];
+      s2 += p[(size_t)(sp + 2) * split_stride];
+      s3 += p[(size_t)(sp + 3) * split_stride];
     }
-    float* w = dW + ((size_t)co * Cin + ci) * KK;
-    for (int j = 0; j < KK; ++j) w[j] = (accumulate ? w[j] : 0.f) + out[j] * scale;
+    for (; sp < nsplit; ++sp) s0 += p[(size_t)sp * split_stride];
+    s_sum[pt][ab_l] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < WB_AB * KK; t += blockDim.x) {
+    const int ab2 = t / KK, j = t % KK;
+    const long long i = i0 + ab2;
+    if (i >= total) continue;
+    float o = 0.f;
+    for (int q = 0; q < npt; ++q) o = fmaf(s_coef[q * KK + j], s_sum[q][ab2], o);
+    const int b = (int)(i % B), a = (int)(i / B);
+    const int co = transpose ? a : b, ci = transpose ? b : a;
+    float* w = dW + ((size_t)co * Cin + ci) * KK + j;
+    *w = (accumulate ? *w : 0.f) + o * scale;
+  }
+}
+
+// Narrow outputs (Cout <= 4, e.g. the gradient wrt the single minibatch-stddev channel): one warp per output pixel
+// and phase, lanes stride over (tap, ci), shuffle reduction.  The 64x64-tiled kernel above would run 8 CTAs with a
+// 4600-step reduction each (260 us for 2.4 MFLOP).
+template <class T>
+__global__ void __launch_bounds__(256) conv_narrow_kernel(const T* __restrict__ x, const T* __restrict__ E,
+                                                          T* __restrict__ y, const float* __restrict__ bias,
+                                                          float bias_mul, int act, SgConvGeom g) {
+  const int lane = threadIdx.x & 31;
+  const long long Q = (long long)g.N * g.Hq * g.Wq;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= Q * g.nphase) return;              // warp-uniform
+  const int ph = (int)(wid % g.nphase);
+  const long long m = wid / g.nphase;
+  const int qx = (int)(m % g.Wq);
+  const long long r = m / g.Wq;
+  const int qy = (int)(r % g.Hq);
+  const int n = (int)(r / g.Hq);
+  const int py = ph >> 1, px = ph & 1;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const T* Eph = E + (size_t)ph * g.ntaps * g.Cin * g.Cout;
+  for (int t = 0; t < g.ntaps; ++t) {
+    const int iy = qy * g.in_stride + g.dy[ph][t];
+    const int ix = qx * g.in_stride + g.dx[ph][t];
+    if (iy < 0 || iy >= g.Hin || ix < 0 || ix >= g.Win) continue;   // warp-uniform
+    const T* xrow = x + (((size_t)n * g.Hin + iy) * g.Win + ix) * g.Cin;
+    const T* Et = Eph + (size_t)t * g.Cin * g.Cout;
+    for (int ci = lane; ci < g.Cin; ci += 32) {
+      const float xv = sg_to_f(xrow[ci]);
+      for (int co = 0; co < g.Cout; ++co) acc[co] = fmaf(xv, sg_to_f(Et[(size_t)ci * g.Cout + co]), acc[co]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co) acc[co] = sg_warp_sum(acc[co]);
+  if (lane < g.Cout) {
+    float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+    if (bias != nullptr) v += bias[lane] * bias_mul;
+    if (act) v = sg_lrelu(v);
+    const int oy = qy * g.out_stride + py, ox = qx * g.out_stride + px;
+    y[(((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout + lane] = sg_from_f<T>(v);
   }
 }
 
@@ -305,6 +367,13 @@ SG_EXPORT int sg_conv_generic(const void* x, const void* E, void* y, const float
   dim3 grid(sg_cdiv(Q, BM), sg_cdiv(g->Cout, BN), g->nphase);
   bool vec = (g->Cin % 4 == 0) && (g->Cout % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g->Cout <= 4 && Q * g->nphase <= (1ll << 22)) {      // narrow output, small map: warp-per-pixel reduction
+    const long long warps = Q * g->nphase;
+    SG_DISPATCH(dtype, {
+      conv_narrow_kernel<T><<<sg_cdiv(warps * 32, 256), 256, 0, st>>>((const T*)x, (const T*)E, (T*)y, bias, bias_mul, act, *g);
+    });
+    return sg_check_launch("sg_conv_generic/narrow");
+  }
   SG_DISPATCH(dtype, {
     if (vec) conv_generic_kernel<T, true><<<grid, NT, 0, st>>>((const T*)x, (const T*)E, (T*)y, bias, bias_mul, act, *g);
     else conv_generic_kernel<T, false><<<grid, NT, 0, st>>>((const T*)x, (const T*)E, (T*)y, bias, bias_mul, act, *g);
@@ -355,7 +424,7 @@ SG_EXPORT int sg_wprep_bwd(const float* partial, int nsplit, float* dW, int Cout
                            const float* coef, float scale, int transpose, int accumulate, void* stream) {
   SG_REQUIRE(KK >= 1 && KK <= 16 && npt >= 1 && nsplit >= 1, "sg_wprep_bwd: bad sizes");
   long long total = (long long)Cout * Cin;
-  wprep_bwd_kernel<<<sg_grid_1d(total, 128), 128, 0, (cudaStream_t)stream>>>(partial, nsplit, dW, Cout, Cin, KK, npt,
+  wprep_bwd_kernel<<<sg_cdiv(total, WB_AB), WB_AB * WB_PT, 0, (cudaStream_t)stream>>>(partial, nsplit, dW, Cout, Cin, KK, npt,
                                                                              coef, scale, transpose, accumulate);
   return sg_check_launch("sg_wprep_bwd");
 }

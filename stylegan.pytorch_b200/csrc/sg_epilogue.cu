@@ -210,15 +210,21 @@ __global__ void affine_nc_kernel(const T* __restrict__ z, const float* __restric
                                  int HW, int C) {
   using V = SgVec<T>;
   const int CV = C / V::N;
-  const long long total = (long long)N * HW * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    long long p = i / CV;
-    int n = (int)(p / HW);
+  const int total = N * HW * CV;                // < 2^31 checked by the launcher
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = i % CV;
+    const int p = i / CV;
+    const int n = p / HW;
     V v, o;
     v.load(z + (size_t)p * C + cv * V::N);
-    const float* q = ab + ((size_t)n * C + cv * V::N) * 3;
+    // the 3*VN coefficients of this channel vector are contiguous and 16-byte aligned: 16-byte loads
+    const float4* q4 = reinterpret_cast<const float4*>(ab + ((size_t)n * C + cv * V::N) * 3);
+    float q[3 * V::N];
+#pragma unroll
+    for (int j = 0; j < 3 * V::N / 4; ++j) {
+      const float4 t = q4[j];
+      q[4 * j] = t.x; q[4 * j + 1] = t.y; q[4 * j + 2] = t.z; q[4 * j + 3] = t.w;
+    }
 #pragma unroll
     for (int k = 0; k < V::N; ++k) o.set(k, fmaf(v.get(k) - q[3 * k], q[3 * k + 1], q[3 * k + 2]));
     o.store(out + (size_t)p * C + cv * V::N);
@@ -257,6 +263,33 @@ __global__ void epi_bwd_finalize_kernel(const double* __restrict__ sums, const f
   coef[(size_t)i * 4 + 1] = -c1 * rstd * B * inv;   // k
   coef[(size_t)i * 4 + 2] = mean;
   coef[(size_t)i * 4 + 3] = -c1 * A * inv;          // c0
+}
+
+// 16-byte vectors of g and z, one float4 of coefficients per channel
+template <class T>
+__global__ void epi_bwd_apply_vec_kernel(const T* __restrict__ g, const T* __restrict__ z,
+                                         const float* __restrict__ coef, T* __restrict__ gy, int N, int HW, int C,
+                                         int act) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const int total = N * HW * CV;                // < 2^31 checked by the launcher
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = i % CV;
+    const int p = i / CV;
+    const int n = p / HW;
+    V vg, vz, o;
+    vg.load(g + (size_t)p * C + cv * V::N);
+    vz.load(z + (size_t)p * C + cv * V::N);
+    const float4* q = reinterpret_cast<const float4*>(coef) + ((size_t)n * C + cv * V::N);
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) {
+      const float4 c4 = q[k];
+      const float zv = vz.get(k);
+      const float gz = fmaf(c4.x, vg.get(k), fmaf(c4.y, zv - c4.z, c4.w));
+      o.set(k, (!act || zv > 0.f) ? gz : SG_LRELU_SLOPE * gz);
+    }
+    o.store(gy + (size_t)p * C + cv * V::N);
+  }
 }
 
 template <class T>
@@ -321,7 +354,7 @@ SG_EXPORT int sg_epi_finalize(const double* sums, const float* style, float* mr,
 SG_EXPORT int sg_affine_nc(const void* z, const float* ab, void* out, int dtype, int N, int HW, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SG_DISPATCH(dtype, {
-    if (C % SgVec<T>::N == 0) {
+    if (C % SgVec<T>::N == 0 && (long long)N * HW * (C / SgVec<T>::N) < (1ll << 30) && ((uintptr_t)ab & 15) == 0) {
       long long total = (long long)N * HW * (C / SgVec<T>::N);
       affine_nc_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)z, ab, (T*)out, N, HW, C);
     } else {
@@ -350,7 +383,11 @@ SG_EXPORT int sg_epi_bwd_apply(const void* g, const void* z, const float* coef, 
   cudaStream_t st = (cudaStream_t)stream;
   long long total = (long long)N * HW * C;
   SG_DISPATCH(dtype, {
-    epi_bwd_apply_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)g, (const T*)z, coef, (T*)gy, N, HW, C, act);
+    const long long tv = total / SgVec<T>::N;
+    if (C % SgVec<T>::N == 0 && tv < (1ll << 30) && ((uintptr_t)coef & 15) == 0)
+      epi_bwd_apply_vec_kernel<T><<<sg_grid_1d(tv, 256, 148 * 16), 256, 0, st>>>((const T*)g, (const T*)z, coef, (T*)gy, N, HW, C, act);
+    else
+      epi_bwd_apply_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)g, (const T*)z, coef, (T*)gy, N, HW, C, act);
   });
   return sg_check_launch("sg_epi_bwd_apply");
 }

@@ -13,13 +13,17 @@ __device__ __forceinline__ float pick4(const float (&a)[4], int k) {
 // depthwise [1,2,1]x[1,2,1]/16 blur, zero pad 1, optional +bias[c]*bias_mul.   reference CustomLayers.py:251-276
 // self-adjoint, so the same kernel is its own backward (without bias).
 // ---------------------------------------------------------------------------------------------------------
-// Each thread owns one 16-byte channel vector of one image column and walks BLUR_STRIP output rows: per input row
-// it loads the 3 horizontal neighbours once, forms the horizontal [1,2,1] sum, and keeps a 3-row window in
-// registers for the vertical [1,2,1] -> 3.75 loads per output instead of 9.
+// Each thread owns one 16-byte channel vector of one image column and walks BLUR_STRIP output rows, keeping a 3-row
+// window of horizontal [1,2,1] sums in registers (3.75 loads per output instead of 9).  The STRIP+2 input rows are
+// fetched in batches of BLUR_BATCH rows x 3 columns = 15 independent 16-byte loads before any arithmetic: with one
+// row (3 loads) in flight per thread the kernel ran at 2.5 TB/s, latency-bound.
 constexpr int BLUR_STRIP = 8;
+constexpr int BLUR_BATCH = 5;
+static_assert((BLUR_STRIP + 2) % BLUR_BATCH == 0, "strip + halo must be a whole number of batches");
 template <class T>
-__global__ void blur3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ bias,
-                             float bias_mul, int N, int H, int W, int C) {
+__global__ void __launch_bounds__(128) blur3_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                    const float* __restrict__ bias, float bias_mul, int N, int H,
+                                                    int W, int C) {
   using V = SgVec<T>;
   const int CV = C / V::N;
   const int strips = (H + BLUR_STRIP - 1) / BLUR_STRIP;
@@ -36,40 +40,46 @@ __global__ void blur3_kernel(const T* __restrict__ x, T* __restrict__ y, const f
     float bb[V::N];
 #pragma unroll
     for (int k = 0; k < V::N; ++k) bb[k] = bias ? bias[cv * V::N + k] * bias_mul : 0.f;
-    float r0[V::N], r1[V::N], r2[V::N];          // horizontal sums of rows h-1, h, h+1
-    auto hsum = [&](int hh, float (&o)[V::N]) {
+    const bool has_l = w > 0, has_r = w + 1 < W;
+    const T* col = x + ((size_t)n * H * W + w) * C + cv * V::N;    // (n, row 0, w, cv)
+    const int off_l = has_l ? -C : 0, off_r = has_r ? C : 0;      // clamped: every load below is unconditional,
+    float r0[V::N] = {}, r1[V::N] = {};                           // so ptxas can issue a whole batch back to back
 #pragma unroll
-      for (int k = 0; k < V::N; ++k) o[k] = 0.f;
-      if (hh < 0 || hh >= H) return;
-      const T* row = x + (((size_t)n * H + hh) * W) * C + cv * V::N;
-      V c;
-      c.load(row + (size_t)w * C);
+    for (int b = 0; b < (BLUR_STRIP + 2) / BLUR_BATCH; ++b) {
+      V raw[BLUR_BATCH][3];
 #pragma unroll
-      for (int k = 0; k < V::N; ++k) o[k] = 2.f * c.get(k);
-      if (w > 0) {
-        V l; l.load(row + (size_t)(w - 1) * C);
-#pragma unroll
-        for (int k = 0; k < V::N; ++k) o[k] += l.get(k);
+      for (int j = 0; j < BLUR_BATCH; ++j) {
+        int hh = h0 - 1 + b * BLUR_BATCH + j;
+        hh = hh < 0 ? 0 : (hh >= H ? H - 1 : hh);
+        const T* row = col + (size_t)hh * W * C;
+        raw[j][0].load(row + off_l);
+        raw[j][1].load(row);
+        raw[j][2].load(row + off_r);
       }
-      if (w + 1 < W) {
-        V q; q.load(row + (size_t)(w + 1) * C);
 #pragma unroll
-        for (int k = 0; k < V::N; ++k) o[k] += q.get(k);
+      for (int j = 0; j < BLUR_BATCH; ++j) {
+        const int ri = b * BLUR_BATCH + j;      // input row h0 - 1 + ri
+        const int hh = h0 - 1 + ri;
+        const bool ok = hh >= 0 && hh < H;
+        float hs[V::N];
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) {
+          const float l = has_l ? raw[j][0].get(k) : 0.f, r = has_r ? raw[j][2].get(k) : 0.f;
+          const float t = (2.f * raw[j][1].get(k) + l) + r;
+          hs[k] = ok ? t : 0.f;
+        }
+        if (ri >= 2) {
+          const int h = h0 + ri - 2;
+          if (h < H) {
+            V o;
+#pragma unroll
+            for (int k = 0; k < V::N; ++k) o.set(k, (r0[k] + 2.f * r1[k] + hs[k]) * (1.f / 16.f) + bb[k]);
+            o.store(y + (((size_t)n * H + h) * W + w) * C + cv * V::N);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) { r0[k] = r1[k]; r1[k] = hs[k]; }
       }
-    };
-    hsum(h0 - 1, r0);
-    hsum(h0, r1);
-#pragma unroll
-    for (int j = 0; j < BLUR_STRIP; ++j) {
-      const int h = h0 + j;
-      if (h >= H) break;
-      hsum(h + 1, r2);
-      V o;
-#pragma unroll
-      for (int k = 0; k < V::N; ++k) o.set(k, (r0[k] + 2.f * r1[k] + r2[k]) * (1.f / 16.f) + bb[k]);
-      o.store(y + (((size_t)n * H + h) * W + w) * C + cv * V::N);
-#pragma unroll
-      for (int k = 0; k < V::N; ++k) { r0[k] = r1[k]; r1[k] = r2[k]; }
     }
   }
 }
@@ -261,13 +271,68 @@ __global__ void __launch_bounds__(256) channel_sum_vec_kernel(const T* __restric
   }
 }
 
-__global__ void partial_reduce_kernel(const float* __restrict__ part, int nblk, int M, float* __restrict__ out,
-                                      float scale, int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
+// Plain per-channel sum (no pixel weights): the bias gradient of every convolution.  Same work split and partial
+// layout as channel_sum_vec_kernel with rows = 1, but 8 independent 16-byte loads per thread and one add per element
+// (the weighted kernel spends 4 FMAs + index arithmetic per element and ran at 1.9 TB/s).
+template <class T>
+__global__ void __launch_bounds__(256) channel_sum_ones_kernel(const T* __restrict__ x, long long P, int C,
+                                                               float* __restrict__ part, int pix_per_blk) {
+  using V = SgVec<T>;
+  extern __shared__ float sm[];                 // [PR][C]
+  const int CV = C / V::N;
+  const int PR = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, pr = threadIdx.x / CV;
+  const long long p0 = (long long)blockIdx.x * pix_per_blk;
+  long long p1 = p0 + pix_per_blk;
+  if (p1 > P) p1 = P;
+  float acc[V::N];
+#pragma unroll
+  for (int k = 0; k < V::N; ++k) acc[k] = 0.f;
+  if (pr < PR) {
+    constexpr int U = 8;                          // the tree below is written for 8
+    const size_t step = (size_t)PR * C;           // elements between this thread's consecutive pixels
+    long long pb = p0 + pr;
+    const T* ptr = x + (size_t)pb * C + cv * V::N;
+    for (; pb + (long long)(U - 1) * PR < p1; pb += (long long)U * PR, ptr += U * step) {
+      V v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u].load(ptr + u * step);      // U independent loads, no predicates
+      // pairwise tree: a serial acc += v[u] chain lets ptxas sink load u to just before its add (3 loads in flight)
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) {
+        const float a = v[0].get(k) + v[1].get(k), b = v[2].get(k) + v[3].get(k);
+        const float c = v[4].get(k) + v[5].get(k), d = v[6].get(k) + v[7].get(k);
+        acc[k] += (a + b) + (c + d);
+      }
+    }
+    for (; pb < p1; pb += PR, ptr += step) {
+      V v;
+      v.load(ptr);
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) acc[k] += v.get(k);
+    }
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) sm[(size_t)pr * C + cv * V::N + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < PR; ++r) s += sm[(size_t)r * C + c];
+    part[(size_t)blockIdx.x * C + c] = s;
+  }
+}
+
+// out[i] = (accumulate ? out[i] : 0) + scale * sum_b part[b][i]: one warp per output element, lanes stride over the
+// partial blocks (one thread walking ~600 partials serially cost 35 us per call).
+__global__ void __launch_bounds__(128) partial_reduce_kernel(const float* __restrict__ part, int nblk, int M,
+                                                             float* __restrict__ out, float scale, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= M) return;                           // warp-uniform
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * M + i];
-  out[i] = (accumulate ? out[i] : 0.f) + s * scale;
+  for (int b = lane; b < nblk; b += 32) s += part[(size_t)b * M + i];
+  s = sg_warp_sum(s);
+  if (lane == 0) out[i] = (accumulate ? out[i] : 0.f) + s * scale;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -282,9 +347,10 @@ __global__ void rgb_in_vec_kernel(const float* __restrict__ img, const float* __
                                   T* __restrict__ y, int N, int HW, int K, int C) {
   using V = SgVec<T>;
   const int CV = C / V::N;
-  const long long total = (long long)N * HW * CV;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cv = (int)(i0 % CV);
+  const int total = N * HW * CV;                 // < 2^31 checked by the launcher
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;     // a multiple of CV
+  const int cv = i0 % CV;
   float wr[V::N][4], br[V::N];
 #pragma unroll
   for (int e = 0; e < V::N; ++e) {
@@ -293,10 +359,10 @@ __global__ void rgb_in_vec_kernel(const float* __restrict__ img, const float* __
 #pragma unroll
     for (int k = 0; k < 4; ++k) wr[e][k] = (k < K) ? Wt[c * K + k] * scale : 0.f;
   }
-  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long p = i / CV;
-    long long n = p / HW;
-    int hw = (int)(p - n * HW);
+  for (int i = i0; i < total; i += stride) {
+    const int p = i / CV;
+    const int n = p / HW;
+    const int hw = p - n * HW;
     float px[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -335,52 +401,73 @@ __global__ void rgb_in_kernel(const float* __restrict__ img, const float* __rest
 // adjoint wrt the image: gimg[n,k,hw] = scale * sum_c g[n,hw,c] * W[c][k]
 // a group of G = min(32, C/VEC) lanes owns one pixel (16-byte loads), xor-shuffle reduction inside the group.
 template <class T>
-__global__ void rgb_in_dgrad_kernel(const T* __restrict__ g, const float* __restrict__ Wt, float scale,
-                                    float* __restrict__ gimg, int N, int HW, int K, int C, int G) {
+__global__ void __launch_bounds__(256) rgb_in_dgrad_kernel(const T* __restrict__ g, const float* __restrict__ Wt,
+                                                           float scale, float* __restrict__ gimg, int N, int HW,
+                                                           int K, int C, int G) {
   using V = SgVec<T>;
-  const long long P = (long long)N * HW;
+  constexpr int U = 4;                           // pixels in flight per lane group
+  const int P = N * HW;                          // < 2^31 checked by the launcher
   const int lane = threadIdx.x & 31;
   const int sub = lane / G, l = lane % G, per_warp = 32 / G;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int CV = C / V::N;
+  const int lc = l < CV ? l : CV - 1;
   // weights of this lane's first channel vector in registers (the only one when CV <= G, the common case)
   float wreg[V::N][4];
 #pragma unroll
   for (int e = 0; e < V::N; ++e)
 #pragma unroll
     for (int k = 0; k < 4; ++k) wreg[e][k] = (l < CV && k < K) ? Wt[(l * V::N + e) * K + k] : 0.f;
-  for (long long p0 = warp * per_warp; p0 < P; p0 += nwarps * per_warp) {
-    const long long p = p0 + sub;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p < P) {
-      if (l < CV) {
-        V v;
-        v.load(g + (size_t)p * C + l * V::N);
+  for (long long q0 = (long long)warp * per_warp * U; q0 < P; q0 += (long long)nwarps * per_warp * U) {
+    V v[U];
 #pragma unroll
-        for (int e = 0; e < V::N; ++e) {
-          float f = v.get(e);
+    for (int u = 0; u < U; ++u) {
+      const long long p = q0 + u * per_warp + sub;   // clamped + unconditional: lanes >= CV carry zero weights and
+      v[u].load(g + (size_t)(p < P ? p : P - 1) * C + lc * V::N);   // pixels >= P are never written
+    }
+    float acc[U][4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[k] = fmaf(f, wreg[e][k], acc[k]);
-        }
-      }
-      for (int cv = l + G; cv < CV; cv += G) {
-        V v;
-        v.load(g + (size_t)p * C + cv * V::N);
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int e = 0; e < V::N; ++e) {
-          float f = v.get(e);
-          const float* wr = Wt + (cv * V::N + e) * K;
-          for (int k = 0; k < K; ++k) acc[k] = fmaf(f, wr[k], acc[k]);
-        }
+      for (int k = 0; k < 4; ++k) acc[u][k] = 0.f;
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) {
+        const float f = v[u].get(e);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[u][k] = fmaf(f, wreg[e][k], acc[u][k]);
       }
     }
-    for (int k = 0; k < K; ++k)
-      for (int o = G >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (p < P && l < K) {
-      long long n = p / HW;
-      int hw = (int)(p - n * HW);
-      gimg[((size_t)n * K + l) * HW + hw] = pick4(acc, l) * scale;
+    if (CV > G) {                                // wide layers (C > 32 vectors): remaining vectors, weights from L1
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = q0 + u * per_warp + sub;
+        if (p < P)
+          for (int cv = l + G; cv < CV; cv += G) {
+            V t;
+            t.load(g + (size_t)p * C + cv * V::N);
+#pragma unroll
+            for (int e = 0; e < V::N; ++e) {
+              const float f = t.get(e);
+              const float* wr = Wt + (cv * V::N + e) * K;
+              for (int k = 0; k < K; ++k) acc[u][k] = fmaf(f, wr[k], acc[u][k]);
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        for (int o = G >> 1; o > 0; o >>= 1) acc[u][k] += __shfl_xor_sync(0xffffffffu, acc[u][k], o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = q0 + u * per_warp + sub;
+      if (p < P && l < K) {
+        const int n = (int)p / HW;
+        const int hw = (int)p - n * HW;
+        gimg[((size_t)n * K + l) * HW + hw] = pick4(acc[u], l) * scale;
+      }
     }
   }
 }
@@ -391,43 +478,80 @@ __global__ void rgb_in_dgrad_kernel(const T* __restrict__ g, const float* __rest
 // reference GAN.py:157,167 (1x1 conv, gain 1), GAN.py:199-202 (temporaryUpsampler + fade-in lerp).
 // ---------------------------------------------------------------------------------------------------------
 template <class T>
-__global__ void rgb_out_kernel(const T* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
-                               float scale, float bias_mul, float alpha, float beta, float* __restrict__ out, int N,
-                               int h, int w, int C, int K, int up, int G) {
+__global__ void __launch_bounds__(256) rgb_out_kernel(const T* __restrict__ x, const float* __restrict__ Wt,
+                                                      const float* __restrict__ bias, float scale, float bias_mul,
+                                                      float alpha, float beta, float* __restrict__ out, int N, int h,
+                                                      int w, int C, int K, int up, int G) {
   using V = SgVec<T>;
-  const long long P = (long long)N * h * w;
+  constexpr int U = 4;                           // pixels in flight per lane group
+  const int P = N * h * w;                       // < 2^31 checked by the launcher
   const int lane = threadIdx.x & 31;
   const int sub = lane / G, l = lane % G, per_warp = 32 / G;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int H = h * up, Wd = w * up, CV = C / V::N;
-  for (long long p0 = warp * per_warp; p0 < P; p0 += nwarps * per_warp) {
-    const long long p = p0 + sub;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p < P) {
-      for (int cv = l; cv < CV; cv += G) {
-        V v;
-        v.load(x + (size_t)p * C + cv * V::N);
+  const int lc = l < CV ? l : CV - 1;
+  float wreg[V::N][4];                           // this lane's first channel vector of W[k][c]
 #pragma unroll
-        for (int e = 0; e < V::N; ++e) {
-          float f = v.get(e);
-          for (int k = 0; k < K; ++k) acc[k] = fmaf(f, Wt[k * C + cv * V::N + e], acc[k]);
-        }
+  for (int e = 0; e < V::N; ++e)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wreg[e][k] = (l < CV && k < K) ? Wt[k * C + l * V::N + e] : 0.f;
+  for (long long q0 = (long long)warp * per_warp * U; q0 < P; q0 += (long long)nwarps * per_warp * U) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = q0 + u * per_warp + sub;   // clamped + unconditional: lanes >= CV carry zero weights and
+      v[u].load(x + (size_t)(p < P ? p : P - 1) * C + lc * V::N);   // pixels >= P are never written
+    }
+    float acc[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[u][k] = 0.f;
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) {
+        const float f = v[u].get(e);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[u][k] = fmaf(f, wreg[e][k], acc[u][k]);
       }
     }
-    for (int k = 0; k < K; ++k)
-      for (int o = G >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (p < P) {
-      int xw = (int)(p % w);
-      long long r = p / w;
-      int yh = (int)(r % h);
-      int n = (int)(r / h);
-      // the group's lanes spread over (k, a, b)
-      for (int j = l; j < K * up * up; j += G) {
-        int k = j / (up * up), ab = j % (up * up), a = ab / up, b = ab % up;
-        float val = alpha * (pick4(acc, k) * scale + (bias ? bias[k] * bias_mul : 0.f));
-        size_t o = (((size_t)n * K + k) * H + (yh * up + a)) * Wd + (xw * up + b);
-        out[o] = (beta != 0.f ? beta * out[o] : 0.f) + val;
+    if (CV > G) {                                // wide layers: remaining vectors, weights from L1
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = q0 + u * per_warp + sub;
+        if (p < P)
+          for (int cv = l + G; cv < CV; cv += G) {
+            V t;
+            t.load(x + (size_t)p * C + cv * V::N);
+#pragma unroll
+            for (int e = 0; e < V::N; ++e) {
+              const float f = t.get(e);
+              for (int k = 0; k < K; ++k) acc[u][k] = fmaf(f, Wt[k * C + cv * V::N + e], acc[u][k]);
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        for (int o = G >> 1; o > 0; o >>= 1) acc[u][k] += __shfl_xor_sync(0xffffffffu, acc[u][k], o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pl = q0 + u * per_warp + sub;
+      if (pl < P) {
+        const int p = (int)pl;
+        const int xw = p % w;
+        const int r = p / w;
+        const int yh = r % h;
+        const int n = r / h;
+        // the group's lanes spread over (k, a, b)
+        for (int j = l; j < K * up * up; j += G) {
+          int k = j / (up * up), ab = j % (up * up), a = ab / up, b = ab % up;
+          float val = alpha * (pick4(acc[u], k) * scale + (bias ? bias[k] * bias_mul : 0.f));
+          size_t o = (((size_t)n * K + k) * H + (yh * up + a)) * Wd + (xw * up + b);
+          out[o] = (beta != 0.f ? beta * out[o] : 0.f) + val;
+        }
       }
     }
   }
@@ -459,6 +583,50 @@ __global__ void rgb_out_dgrad_kernel(const float* __restrict__ g, const float* _
       float s_ = 0.f;
       for (int k = 0; k < K; ++k) s_ = fmaf(Wt[k * C + cv * V::N + e], gs[k], s_);
       o.set(e, s_ * coef);
+    }
+    o.store(gx + (size_t)p * C + cv * V::N);
+  }
+}
+
+// same, launched with gridDim*blockDim a multiple of CV: a thread keeps one channel vector for its whole grid-stride
+// loop, so W*coef lives in registers and the index arithmetic is 32-bit.
+template <class T>
+__global__ void rgb_out_dgrad_vec_kernel(const float* __restrict__ g, const float* __restrict__ Wt, float coef,
+                                         T* __restrict__ gx, int N, int h, int w, int C, int K, int up) {
+  using V = SgVec<T>;
+  const int CV = C / V::N;
+  const int total = N * h * w * CV;              // < 2^31 checked by the launcher
+  const int H = h * up, Wd = w * up;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;     // a multiple of CV
+  const int cv = i0 % CV;
+  float wr[V::N][4];
+#pragma unroll
+  for (int e = 0; e < V::N; ++e)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wr[e][k] = (k < K) ? Wt[k * C + cv * V::N + e] * coef : 0.f;
+  for (int i = i0; i < total; i += stride) {
+    const int p = i / CV;
+    const int xw = p % w;
+    const int r = p / w;
+    const int yh = r % h;
+    const int n = r / h;
+    float gs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < K) {
+        const float* gp = g + (((size_t)n * K + k) * H + (size_t)yh * up) * Wd + (size_t)xw * up;
+        float t = gp[0];
+        if (up == 2) t += gp[1] + gp[Wd] + gp[Wd + 1];
+        gs[k] = t;
+      }
+    V o;
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) {
+      float s_ = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_ = fmaf(wr[e][k], gs[k], s_);
+      o.set(e, s_);
     }
     o.store(gx + (size_t)p * C + cv * V::N);
   }
@@ -743,7 +911,10 @@ SG_EXPORT int sg_channel_sum(const void* x, int dtype, const float* wt, int J, i
     const int CV = C / VN;
     if (C % VN == 0 && CV <= 256 && (size_t)rows * (256 / CV) * C * sizeof(float) <= 48 * 1024) {
       size_t smv = (size_t)rows * (256 / CV) * C * sizeof(float);
-      channel_sum_vec_kernel<T><<<nblk, 256, smv, st>>>((const T*)x, wt, J, ones, P, HW, C, part_ws, pix_per_blk);
+      if (J == 0)
+        channel_sum_ones_kernel<T><<<nblk, 256, smv, st>>>((const T*)x, P, C, part_ws, pix_per_blk);
+      else
+        channel_sum_vec_kernel<T><<<nblk, 256, smv, st>>>((const T*)x, wt, J, ones, P, HW, C, part_ws, pix_per_blk);
     } else {
       channel_sum_kernel<T><<<nblk, block, smem, st>>>((const T*)x, wt, J, ones, P, HW, C, part_ws, pix_per_blk);
     }
@@ -751,7 +922,7 @@ SG_EXPORT int sg_channel_sum(const void* x, int dtype, const float* wt, int J, i
   int rc = sg_check_launch("sg_channel_sum");
   if (rc) return rc;
   int M = rows * C;
-  partial_reduce_kernel<<<sg_cdiv(M, 128), 128, 0, st>>>(part_ws, nblk, M, out, scale, accumulate);
+  partial_reduce_kernel<<<sg_cdiv(M, 4), 128, 0, st>>>(part_ws, nblk, M, out, scale, accumulate);
   return sg_check_launch("sg_channel_sum/reduce");
 }
 
@@ -761,7 +932,7 @@ SG_EXPORT int sg_rgb_in(const float* img, const float* W, const float* bias, flo
   cudaStream_t st = (cudaStream_t)stream;
   long long total = (long long)N * HW * C;
   SG_DISPATCH(dtype, {
-    if (C % SgVec<T>::N == 0 && 256 % (C / SgVec<T>::N) == 0)     // 256 threads per block, CV | 256 -> fixed cv per thread
+    if (C % SgVec<T>::N == 0 && 256 % (C / SgVec<T>::N) == 0 && total / SgVec<T>::N < (1ll << 30))   // CV | 256 -> fixed cv per thread
       rgb_in_vec_kernel<T><<<sg_grid_1d(total / SgVec<T>::N, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);
     else
       rgb_in_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(img, W, bias, scale, bias_mul, act, (T*)y, N, HW, K, C);
@@ -779,7 +950,8 @@ SG_EXPORT int sg_rgb_in_dgrad(const void* g, int dtype, const float* W, float sc
     int G = 1;
     while (G < 32 && G < C / SgVec<T>::N) G <<= 1;
     if (G < 4) G = 4;                       // K <= 4 writer lanes
-    rgb_in_dgrad_kernel<T><<<sg_grid_1d(P * G, 256, 148 * 16), 256, 0, st>>>((const T*)g, W, scale, gimg, N, HW, K, C, G);
+    SG_REQUIRE(P < (1ll << 30), "sg_rgb_in_dgrad: too many pixels");
+    rgb_in_dgrad_kernel<T><<<sg_grid_1d((P * G + 3) / 4, 256, 148 * 8), 256, 0, st>>>((const T*)g, W, scale, gimg, N, HW, K, C, G);
   });
   return sg_check_launch("sg_rgb_in_dgrad");
 }
@@ -793,7 +965,8 @@ SG_EXPORT int sg_rgb_out(const void* x, int dtype, const float* W, const float* 
     SG_REQUIRE(C % SgVec<T>::N == 0, "sg_rgb_out: C must be a multiple of the 16-byte vector width");
     int G = 1;
     while (G < 32 && G < C / SgVec<T>::N) G <<= 1;
-    rgb_out_kernel<T><<<sg_grid_1d(P * G, 256, 148 * 16), 256, 0, st>>>((const T*)x, W, bias, scale, bias_mul, alpha, beta, out, N, h, w, C, K, up, G);
+    SG_REQUIRE(P < (1ll << 30), "sg_rgb_out: too many pixels");
+    rgb_out_kernel<T><<<sg_grid_1d((P * G + 3) / 4, 256, 148 * 8), 256, 0, st>>>((const T*)x, W, bias, scale, bias_mul, alpha, beta, out, N, h, w, C, K, up, G);
   });
   return sg_check_launch("sg_rgb_out");
 }
@@ -805,7 +978,10 @@ SG_EXPORT int sg_rgb_out_dgrad(const float* g, const float* W, float coef, void*
   SG_DISPATCH(dtype, {
     SG_REQUIRE(C % SgVec<T>::N == 0, "sg_rgb_out_dgrad: C must be a multiple of the 16-byte vector width");
     long long total = (long long)N * h * w * (C / SgVec<T>::N);
-    rgb_out_dgrad_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(g, W, coef, (T*)gx, N, h, w, C, K, up);
+    if (256 % (C / SgVec<T>::N) == 0 && total < (1ll << 30))
+      rgb_out_dgrad_vec_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(g, W, coef, (T*)gx, N, h, w, C, K, up);
+    else
+      rgb_out_dgrad_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>(g, W, coef, (T*)gx, N, h, w, C, K, up);
   });
   return sg_check_launch("sg_rgb_out_dgrad");
 }

@@ -53,7 +53,8 @@ def _ref_conv(kind, x, W, scale):
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("kind,k,ci,co,hw", [("same", 3, 16, 24, 12), ("same", 1, 8, 12, 8), ("down", 3, 16, 32, 16),
                                               ("up", 3, 32, 16, 8), ("up_fused", 3, 8, 4, 64), ("same", 3, 9, 8, 4),
-                                              ("same", 3, 64, 64, 32), ("down", 3, 4, 8, 128)])
+                                              ("same", 3, 64, 64, 32), ("down", 3, 4, 8, 128),
+                                              ("same", 3, 40, 1, 8), ("same", 3, 1, 40, 8)])
 def test_conv_forward_backward(kind, k, ci, co, hw, dt):
     from models import _ops
     torch.manual_seed(0)
@@ -140,6 +141,64 @@ def test_blur_and_axpby(dt):
     assert rel(nchw(gx), gx_ref) < TOL[dt] and rel(gb, gb_ref) < TOL[dt]
     z = _ops.Axpby.apply(xd, y, 0.3, 0.7)
     assert rel(nchw(z), 0.3 * xr + 0.7 * y_ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 16, 9, 7), (1, 64, 20, 5), (3, 8, 4, 4), (1, 256, 17, 3), (2, 64, 25, 20)])
+def test_blur_vector_path_odd_sizes(dt, shape):
+    """Strip/batch logic of blur3_kernel: heights that are not a multiple of the 8-row strip, 1-3 pixel wide borders,
+    the 16-byte vector path in both dtypes; and the plain per-channel sum (bias gradient) on the same odd sizes."""
+    from models import _ops
+    torch.manual_seed(11)
+    x = torch.randn(*shape)
+    if dt == torch.bfloat16:
+        x = x.bfloat16().float()
+    xd = nhwc(x, dt)
+    y = _ops.Blur.apply(xd, None, 1.0)
+    assert rel(nchw(y), O.blur3(x)) < TOL[dt]
+    s = _ops.ChannelSum.apply(xd, None, True, 0.5)
+    assert rel(s.reshape(-1), 0.5 * x.sum(dim=(0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,C,hw", [(1, 24, 5), (3, 8, 7), (2, 64, 6), (1, 512, 4)])
+def test_rgb_kernels_ragged_sizes(dt, N, C, hw):
+    """to_rgb / from_rgb adjoints with pixel counts that do not fill the last lane group, channel-vector counts that
+    are not a power of two (idle lanes), and C wider than one warp of vectors (second-pass loop)."""
+    from models import _ops
+    torch.manual_seed(12)
+    x_hi, x_lo = torch.randn(N, C, hw * 2, hw * 2), torch.randn(N, C, hw, hw)
+    if dt == torch.bfloat16:
+        x_hi, x_lo = x_hi.bfloat16().float(), x_lo.bfloat16().float()
+    Wh, bh, Wl, bl = torch.randn(3, C, 1, 1), torch.randn(3), torch.randn(3, C, 1, 1), torch.randn(3)
+    leaves = [t.clone().requires_grad_(True) for t in (x_hi, Wh, bh, x_lo, Wl, bl)]
+    a = 0.6
+    out_ref = a * O.eq_conv(leaves[0], leaves[1], leaves[2], 1.0) + \
+        (1 - a) * O.eq_conv(O.nearest_up2(leaves[3]), leaves[4], leaves[5], 1.0)
+    g = torch.randn_like(out_ref)
+    ref_grads = torch.autograd.grad(out_ref, leaves, g)
+    dl = [nhwc(x_hi, dt).requires_grad_(True), torch.nn.Parameter(Wh.to(DEV)), torch.nn.Parameter(bh.to(DEV)),
+          nhwc(x_lo, dt).requires_grad_(True), torch.nn.Parameter(Wl.to(DEV)), torch.nn.Parameter(bl.to(DEV))]
+    out = _ops.ToRgb.apply(dl[0], dl[1], dl[2], O.he_scale(C, 1.0), a, dl[3], dl[4], dl[5], O.he_scale(C, 1.0), 1 - a)
+    assert rel(out, out_ref) < TOL[dt]
+    grads = torch.autograd.grad(out, dl, g.to(DEV))
+    assert rel(nchw(grads[0]), ref_grads[0]) < TOL[dt] and rel(nchw(grads[3]), ref_grads[3]) < TOL[dt]
+    for i in (1, 2, 4, 5):
+        assert rel(grads[i], ref_grads[i]) < TOL[dt]
+    # from_rgb and its image gradient
+    img = torch.randn(N, 3, hw, hw)
+    W, b = torch.randn(C, 3, 1, 1), torch.randn(C)
+    lv = [t.clone().requires_grad_(True) for t in (img, W, b)]
+    y_ref = O.eq_conv(lv[0], lv[1], lv[2], math.sqrt(2))
+    gy = torch.randn_like(y_ref)
+    rg = torch.autograd.grad(y_ref, lv, gy)
+    imgd = img.to(DEV).requires_grad_(True)
+    Wd, bd = torch.nn.Parameter(W.to(DEV)), torch.nn.Parameter(b.to(DEV))
+    y = _ops.RgbIn.apply(imgd, Wd, bd, O.he_scale(3, math.sqrt(2)), 1.0, False, dt)
+    assert rel(nchw(y), y_ref) < TOL[dt]
+    gr = torch.autograd.grad(y, [imgd, Wd, bd], nhwc(gy, dt))
+    for u, v in zip(gr, rg):
+        assert rel(u, v) < TOL[dt]
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])

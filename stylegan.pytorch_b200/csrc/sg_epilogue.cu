@@ -205,29 +205,43 @@ __global__ void epi_finalize_kernel(const double* __restrict__ sums, const float
 }
 
 // out[n,p,c] = (z - mab[n,c,0]) * mab[n,c,1] + mab[n,c,2]
+// grid (pixel chunks, N), blockDim a multiple of CV: a thread keeps one channel vector of one image for its whole
+// loop, so its 3*VN coefficients are loaded once into registers (a per-pixel gather of them from L1 -- 8 distinct
+// lines per warp instruction -- held these kernels at 1.6-4 TB/s).
 template <class T>
-__global__ void affine_nc_kernel(const T* __restrict__ z, const float* __restrict__ ab, T* __restrict__ out, int N,
-                                 int HW, int C) {
+__global__ void __launch_bounds__(256) affine_nc_kernel(const T* __restrict__ z, const float* __restrict__ ab,
+                                                        T* __restrict__ out, int HW, int C, int pix_per_blk) {
   using V = SgVec<T>;
   const int CV = C / V::N;
-  const int total = N * HW * CV;                // < 2^31 checked by the launcher
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int cv = i % CV;
-    const int p = i / CV;
-    const int n = p / HW;
-    V v, o;
-    v.load(z + (size_t)p * C + cv * V::N);
-    // the 3*VN coefficients of this channel vector are contiguous and 16-byte aligned: 16-byte loads
-    const float4* q4 = reinterpret_cast<const float4*>(ab + ((size_t)n * C + cv * V::N) * 3);
-    float q[3 * V::N];
+  const int n = blockIdx.y;
+  const int cv = threadIdx.x % CV, pr = threadIdx.x / CV, PR = blockDim.x / CV;
+  const int p0 = blockIdx.x * pix_per_blk;
+  int p1 = p0 + pix_per_blk;
+  if (p1 > HW) p1 = HW;
+  float q[3 * V::N];
 #pragma unroll
-    for (int j = 0; j < 3 * V::N / 4; ++j) {
-      const float4 t = q4[j];
-      q[4 * j] = t.x; q[4 * j + 1] = t.y; q[4 * j + 2] = t.z; q[4 * j + 3] = t.w;
+  for (int j = 0; j < 3 * V::N; ++j) q[j] = ab[((size_t)n * C + cv * V::N) * 3 + j];
+  const size_t base = ((size_t)n * HW) * C + cv * V::N;
+  constexpr int U = 4;
+  int p = p0 + pr;
+  for (; p + (U - 1) * PR < p1; p += U * PR) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u].load(z + base + (size_t)(p + u * PR) * C);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      V o;
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) o.set(k, fmaf(v[u].get(k) - q[3 * k], q[3 * k + 1], q[3 * k + 2]));
+      o.store(out + base + (size_t)(p + u * PR) * C);
     }
+  }
+  for (; p < p1; p += PR) {
+    V v, o;
+    v.load(z + base + (size_t)p * C);
 #pragma unroll
     for (int k = 0; k < V::N; ++k) o.set(k, fmaf(v.get(k) - q[3 * k], q[3 * k + 1], q[3 * k + 2]));
-    o.store(out + (size_t)p * C + cv * V::N);
+    o.store(out + base + (size_t)p * C);
   }
 }
 template <class T>
@@ -265,30 +279,55 @@ __global__ void epi_bwd_finalize_kernel(const double* __restrict__ sums, const f
   coef[(size_t)i * 4 + 3] = -c1 * A * inv;          // c0
 }
 
-// 16-byte vectors of g and z, one float4 of coefficients per channel
+// same launch scheme as affine_nc_kernel: the 4*VN coefficients of (n, channel vector) live in registers
 template <class T>
-__global__ void epi_bwd_apply_vec_kernel(const T* __restrict__ g, const T* __restrict__ z,
-                                         const float* __restrict__ coef, T* __restrict__ gy, int N, int HW, int C,
-                                         int act) {
+__global__ void __launch_bounds__(256) epi_bwd_apply_vec_kernel(const T* __restrict__ g, const T* __restrict__ z,
+                                                                const float* __restrict__ coef, T* __restrict__ gy,
+                                                                int HW, int C, int pix_per_blk, int act) {
   using V = SgVec<T>;
   const int CV = C / V::N;
-  const int total = N * HW * CV;                // < 2^31 checked by the launcher
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int cv = i % CV;
-    const int p = i / CV;
-    const int n = p / HW;
-    V vg, vz, o;
-    vg.load(g + (size_t)p * C + cv * V::N);
-    vz.load(z + (size_t)p * C + cv * V::N);
-    const float4* q = reinterpret_cast<const float4*>(coef) + ((size_t)n * C + cv * V::N);
+  const int n = blockIdx.y;
+  const int cv = threadIdx.x % CV, pr = threadIdx.x / CV, PR = blockDim.x / CV;
+  const int p0 = blockIdx.x * pix_per_blk;
+  int p1 = p0 + pix_per_blk;
+  if (p1 > HW) p1 = HW;
+  float c1[V::N], ck[V::N], cm[V::N], c0[V::N];
+#pragma unroll
+  for (int k = 0; k < V::N; ++k) {
+    const float* q = coef + ((size_t)n * C + cv * V::N + k) * 4;
+    c1[k] = q[0]; ck[k] = q[1]; cm[k] = q[2]; c0[k] = q[3];
+  }
+  const size_t base = ((size_t)n * HW) * C + cv * V::N;
+  auto apply = [&](const V& vg, const V& vz, V& o) {
 #pragma unroll
     for (int k = 0; k < V::N; ++k) {
-      const float4 c4 = q[k];
       const float zv = vz.get(k);
-      const float gz = fmaf(c4.x, vg.get(k), fmaf(c4.y, zv - c4.z, c4.w));
+      const float gz = fmaf(c1[k], vg.get(k), fmaf(ck[k], zv - cm[k], c0[k]));
       o.set(k, (!act || zv > 0.f) ? gz : SG_LRELU_SLOPE * gz);
     }
-    o.store(gy + (size_t)p * C + cv * V::N);
+  };
+  constexpr int U = 2;
+  int p = p0 + pr;
+  for (; p + (U - 1) * PR < p1; p += U * PR) {
+    V vg[U], vz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      vg[u].load(g + base + (size_t)(p + u * PR) * C);
+      vz[u].load(z + base + (size_t)(p + u * PR) * C);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      V o;
+      apply(vg[u], vz[u], o);
+      o.store(gy + base + (size_t)(p + u * PR) * C);
+    }
+  }
+  for (; p < p1; p += PR) {
+    V vg, vz, o;
+    vg.load(g + base + (size_t)p * C);
+    vz.load(z + base + (size_t)p * C);
+    apply(vg, vz, o);
+    o.store(gy + base + (size_t)p * C);
   }
 }
 
@@ -351,12 +390,25 @@ SG_EXPORT int sg_epi_finalize(const double* sums, const float* style, float* mr,
   return sg_check_launch("sg_epi_finalize");
 }
 
+// (pixel chunks, N) grid for the register-coefficient kernels: >= ~8 CTAs per SM overall, >= 64 pixels per CTA
+static void per_image_grid(int N, int HW, int* chunks, int* pix_per_blk) {
+  int c = (148 * 8 + N - 1) / N;
+  const int maxc = (HW + 63) / 64;
+  if (c > maxc) c = maxc;
+  if (c < 1) c = 1;
+  *pix_per_blk = (HW + c - 1) / c;
+  *chunks = (HW + *pix_per_blk - 1) / *pix_per_blk;
+}
+
 SG_EXPORT int sg_affine_nc(const void* z, const float* ab, void* out, int dtype, int N, int HW, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SG_DISPATCH(dtype, {
-    if (C % SgVec<T>::N == 0 && (long long)N * HW * (C / SgVec<T>::N) < (1ll << 30) && ((uintptr_t)ab & 15) == 0) {
-      long long total = (long long)N * HW * (C / SgVec<T>::N);
-      affine_nc_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)z, ab, (T*)out, N, HW, C);
+    const int VN = SgVec<T>::N;
+    if (C % VN == 0 && C / VN <= 256 && N <= 65535) {
+      const int CV = C / VN;
+      int chunks, ppb;
+      per_image_grid(N, HW, &chunks, &ppb);
+      affine_nc_kernel<T><<<dim3(chunks, N), (256 / CV) * CV, 0, st>>>((const T*)z, ab, (T*)out, HW, C, ppb);
     } else {
       long long total = (long long)N * HW * C;
       affine_nc_scalar_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)z, ab, (T*)out, N, HW, C);
@@ -383,11 +435,15 @@ SG_EXPORT int sg_epi_bwd_apply(const void* g, const void* z, const float* coef, 
   cudaStream_t st = (cudaStream_t)stream;
   long long total = (long long)N * HW * C;
   SG_DISPATCH(dtype, {
-    const long long tv = total / SgVec<T>::N;
-    if (C % SgVec<T>::N == 0 && tv < (1ll << 30) && ((uintptr_t)coef & 15) == 0)
-      epi_bwd_apply_vec_kernel<T><<<sg_grid_1d(tv, 256, 148 * 16), 256, 0, st>>>((const T*)g, (const T*)z, coef, (T*)gy, N, HW, C, act);
-    else
+    const int VN = SgVec<T>::N;
+    if (C % VN == 0 && C / VN <= 256 && N <= 65535) {
+      const int CV = C / VN;
+      int chunks, ppb;
+      per_image_grid(N, HW, &chunks, &ppb);
+      epi_bwd_apply_vec_kernel<T><<<dim3(chunks, N), (256 / CV) * CV, 0, st>>>((const T*)g, (const T*)z, coef, (T*)gy, HW, C, ppb, act);
+    } else {
       epi_bwd_apply_kernel<T><<<sg_grid_1d(total, 256, 148 * 32), 256, 0, st>>>((const T*)g, (const T*)z, coef, (T*)gy, N, HW, C, act);
+    }
   });
   return sg_check_launch("sg_epi_bwd_apply");
 }

@@ -359,24 +359,31 @@ __global__ void rgb_in_vec_kernel(const float* __restrict__ img, const float* __
 #pragma unroll
     for (int k = 0; k < 4; ++k) wr[e][k] = (k < K) ? Wt[c * K + k] * scale : 0.f;
   }
-  for (int i = i0; i < total; i += stride) {
-    const int p = i / CV;
-    const int n = p / HW;
-    const int hw = p - n * HW;
-    float px[4] = {0.f, 0.f, 0.f, 0.f};
+  // two pixels per iteration: the image loads of both are issued before either result is formed
+  for (int i = i0; i < total; i += 2 * stride) {
+    const bool ok2 = i + stride < total;
+    const int pa = i / CV, pb = (ok2 ? i + stride : i) / CV;
+    const int na = pa / HW, nb = pb / HW;
+    const int ha = pa - na * HW, hb = pb - nb * HW;
+    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (k < K) px[k] = img[((size_t)n * K + k) * HW + hw];
-    V o;
+      if (k < K) {
+        xa[k] = img[((size_t)na * K + k) * HW + ha];
+        xb[k] = img[((size_t)nb * K + k) * HW + hb];
+      }
+    V oa, ob;
 #pragma unroll
     for (int e = 0; e < V::N; ++e) {
-      float s = br[e];
+      float sa = br[e], sb = br[e];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s = fmaf(wr[e][k], px[k], s);
-      if (act) s = sg_lrelu(s);
-      o.set(e, s);
+      for (int k = 0; k < 4; ++k) { sa = fmaf(wr[e][k], xa[k], sa); sb = fmaf(wr[e][k], xb[k], sb); }
+      if (act) { sa = sg_lrelu(sa); sb = sg_lrelu(sb); }
+      oa.set(e, sa);
+      ob.set(e, sb);
     }
-    o.store(y + (size_t)p * C + cv * V::N);
+    oa.store(y + (size_t)pa * C + cv * V::N);
+    if (ok2) ob.store(y + (size_t)pb * C + cv * V::N);
   }
 }
 

@@ -49,6 +49,7 @@ class ClockSampler:
         self.samples = []
         self.reasons = set()
         self._stop = False
+        self.period = float(os.environ.get("SG_BENCH_SAMPLE_MS", "200")) * 1e-3
 
     def _nvml_loop(self, nv, h):
         while not self._stop:
@@ -60,7 +61,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(self.period)
 
     def start(self):
         try:

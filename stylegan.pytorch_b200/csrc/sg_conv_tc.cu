@@ -219,8 +219,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-// N block: 128 whenever Cout allows it (a 128x128x16 MMA reads 8 KB of operands in its 64 tensor cycles, while N = 64
-// is bound by shared-memory operand bandwidth), otherwise the whole Cout (16..112).
+// N block: 128 whenever Cout allows it, otherwise the whole Cout (16..112).  A 128xNx16 SS-mode MMA costs ~61 cycles
+// plus ~0.15 cycles per column (measured: N=64 67.9, N=128 79.9, N=256 130.4 cycles, tools/mma_rate.cu), so the
+// work per instruction should be as large as the accumulator budget allows.
 static int pick_bn(int Cin, int Cout) {
   (void)Cin;
   if (Cout % 128 == 0) return 128;

@@ -213,13 +213,17 @@ def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    batch = args.ref_batch
+    # bounded sample: one CPU step at 256x256 costs ~12 s per image on a 64-thread host, so a K+W of more than a handful
+    # of steps runs at batch 1 and with a single warm-up step (the CPU path has no autotuning or lazy initialisation to
+    # absorb); the JSON line reports the warm-up actually run
+    batch = args.ref_batch if args.steps + args.warmup <= 4 else 1
+    args.warmup = min(args.warmup, 1)
     times, threads = cpu_oracle_step_time(args.res, batch, args.steps, args.warmup)
     sec = sum(times) / len(times)
     val = batch / sec
     out = {"impl": "reference", "metric": "images/sec G+D step @%dx%d bs=%d/GPU" % (args.res, args.res, args.batch),
            "value": round(val, 4),
-           "unit": "images/sec", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+           "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": "G+D step (logistic+R1, EMA) %dx%d depth %d" % (args.res, args.res, O_depth(args.res)),

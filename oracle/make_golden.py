@@ -166,6 +166,35 @@ def golden_forward_backward(name, arch, batch, depth, alpha, seed=1):
           (fx["d_loss"], fx["g_loss"], fx["r1"]))
 
 
+def golden_other_losses(name, arch, batch, depth, alpha, seed=3):
+    """Hinge and relativistic-average hinge (models/Losses.py:136-189) evaluated by the reference's own loss classes
+    on its Discriminator: losses plus the gradient norms wrt every discriminator parameter."""
+    from models.Losses import HingeGAN, RelativisticAverageHingeGAN
+    seed_all(seed)
+    sg = build_reference(arch)
+    randomize_zero_inits(sg)
+    sg.dis.train()
+    res = 2 ** (depth + 2)
+    real = torch.randn(batch, arch.num_channels, res, res)
+    fake = torch.randn(batch, arch.num_channels, res, res)
+    dn = [n for n, _ in sg.dis.named_parameters()]
+    fx = dict(arch=arch.__dict__.copy(), batch=batch, depth=depth, alpha=alpha, d_init=clone_sd(sg.dis.state_dict()),
+              real=real, fake=fake, losses={})
+    for key, cls in (("hinge", HingeGAN), ("relativistic-hinge", RelativisticAverageHingeGAN)):
+        L = cls(sg.dis)
+        dl = L.dis_loss(real, fake, depth, alpha)
+        gl = L.gen_loss(real, fake, depth, alpha)
+        dg = torch.autograd.grad(dl, list(sg.dis.parameters()), allow_unused=True)
+        gg = torch.autograd.grad(gl, list(sg.dis.parameters()), allow_unused=True)
+        fx["losses"][key] = dict(d_loss=float(dl.detach()), g_loss=float(gl.detach()),
+                                 d_grad_norms={n: float(g.norm()) for n, g in zip(dn, dg) if g is not None},
+                                 g_grad_norms={n: float(g.norm()) for n, g in zip(dn, gg) if g is not None})
+    out = os.path.join(ROOT, "tests", "golden", name + ".pt")
+    torch.save(fx, out)
+    print(name, "->", out, "%.1f KB" % (os.path.getsize(out) / 1024),
+          {k: (round(v["d_loss"], 5), round(v["g_loss"], 5)) for k, v in fx["losses"].items()})
+
+
 def live_full_width(outdir):
     """BASELINE config 1 at the reference's real channel widths (too large to commit): resolution-128 config,
     depth 1 (8x8) and depth 2 (16x16), batch 4.  Used by tests/test_oracle_vs_reference.py in the build container."""
@@ -191,6 +220,8 @@ def main():
                      fmap_max=16)
     golden_forward_backward("fb_tiny128_d5", tiny128, batch=4, depth=5, alpha=0.5)
     golden_forward_backward("fb_tiny128_d4", tiny128, batch=4, depth=4, alpha=0.3, seed=2)
+    # the other loss classes the reference ships (configs: loss = 'hinge' | 'relativistic-hinge')
+    golden_other_losses("losses_tiny16_d2", tiny16, batch=4, depth=2, alpha=0.5)
 
 
 if __name__ == "__main__":

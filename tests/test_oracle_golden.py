@@ -97,6 +97,30 @@ def test_trajectory(golden_dir):
         assert st.d_opt.steps[k] == fx["d_adam_step"][k], k
 
 
+@pytest.mark.parametrize("loss_name", ["hinge", "relativistic-hinge"])
+def test_other_losses(golden_dir, loss_name):
+    """Hinge / relativistic-average hinge of the oracle against the reference's loss classes (models/Losses.py:136-189):
+    loss values and the gradient norm of every discriminator parameter."""
+    fx = load(golden_dir, "losses_tiny16_d2")
+    arch = arch_from(fx["arch"])
+    d = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["d_init"].items()}
+    depth, alpha, real, fake = fx["depth"], fx["alpha"], fx["real"], fx["fake"]
+    ref = fx["losses"][loss_name]
+    if loss_name == "hinge":
+        dl, gl = O.d_loss_hinge(d, real, fake, depth, alpha, arch), O.g_loss_hinge(d, fake, depth, alpha, arch)
+    else:
+        dl = O.d_loss_rahinge(d, real, fake, depth, alpha, arch)
+        gl = O.g_loss_rahinge(d, real, fake, depth, alpha, arch)
+    assert abs(float(dl) - ref["d_loss"]) <= TOL * abs(ref["d_loss"])
+    assert abs(float(gl) - ref["g_loss"]) <= TOL * abs(ref["g_loss"])
+    for loss, norms in ((dl, ref["d_grad_norms"]), (gl, ref["g_grad_norms"])):
+        names = [k for k in norms]
+        grads = torch.autograd.grad(loss, [d[k] for k in names], allow_unused=True, retain_graph=True)
+        for k, g in zip(names, grads):
+            got = 0.0 if g is None else float(g.norm())
+            assert abs(got - norms[k]) <= 1e-3 * norms[k] + 1e-7, (loss_name, k, got, norms[k])
+
+
 def test_state_dict_key_contract():
     """86/48 keys at 128, 99/56 at 256, 125/72 at 1024 (avg_latent absent when psi<=0)."""
     for res, ng, nd in ((128, 86, 48), (256, 99, 56), (1024, 125, 72)):

@@ -7,9 +7,8 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------------------
 // y[b][o] = act(scale * sum_i x[b*ldx + i] * W[o][i] + bias[o]*bias_mul)        reference CustomLayers.py:99-103
-// one warp per output feature o, 8 batch rows at a time.
+// one warp per output feature o.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LIN_BB = 8;
 constexpr int LF_OB = 8;      // outputs per block (one warp each)
 constexpr int LF_IC = 256;    // input chunk staged in shared memory
 constexpr int LF_BMAX = 32;   // batch rows per pass

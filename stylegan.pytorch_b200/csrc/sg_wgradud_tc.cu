@@ -23,7 +23,7 @@ constexpr int DY_BLOCK_BYTES = TH * TW * 128;          // 16384
 constexpr int X_BLOCK_BYTES = (TH + 1) * TW * 128;     // 18432
 constexpr int NUM_THREADS = 192;
 constexpr int MAX_STAGES = 8;
-constexpr int MODE_UP = 0, MODE_DOWN = 1;
+constexpr int MODE_UP = 0;                        // mode 1 = DOWN (include/sgb200.h)
 
 struct __align__(8) Barriers {
   uint64_t full[MAX_STAGES];

@@ -23,6 +23,8 @@ sys.path.insert(0, os.path.join(ROOT, "stylegan.pytorch_b200"))
 sys.dont_write_bytecode = True
 
 F_STEP_GFLOP = {128: 656.7, 256: 822.8, 1024: 1162.0}     # BASELINE.md section 3 (reference formulation, per image)
+# executed by this engine: 4 F_G + 11 F_D (the logistic term and the R1 penalty share one D(real) graph, Losses.py)
+F_EXEC_GFLOP = {128: 547.3, 256: 685.7, 1024: 968.4}
 
 
 def peaks():
@@ -346,12 +348,14 @@ def main():
                "config": {"workload": "StyleGAN G+D step (optimize_discriminator + optimize_generator, logistic + R1, "
                                       "EMA, style mixing, truncation) %dx%d depth %d alpha 0.5" % (R, R, depth),
                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                          "shared_real_pass": True,
                           "l2": "per-step activations (GBs) exceed the 126 MB L2; no explicit flush"},
                "e2e": {"value": round(e2e, 2), "unit": "images/sec", "ms_per_step": round(ms_e2e / args.steps, 3),
                        "h2d_bytes_per_step": B * 3 * R * R * 4 + B * 512 * 4, "d2h_bytes_per_step": 8},
                "gpu_launches": int(launches), "clocks": clocks}
         if fstep:
             out["step_tensor_fraction"] = {"algorithmic_gflop_per_image": fstep,
+                                           "executed_gflop_per_image": F_EXEC_GFLOP.get(R),
                                            "achieved_tflops_per_gpu": round(value / world * fstep / 1e3, 1),
                                            "frac_of_sustained_bf16_peak": round(value / world * fstep / 1e3 /
                                                                                 pk["bf16_tflops_sustained"], 4),

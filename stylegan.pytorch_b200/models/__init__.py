@@ -28,3 +28,10 @@ def set_precision(p):
 def precision():
     from ._ops import precision as _p
     return _p()
+
+
+def set_shared_r1(flag):
+    """Evaluate D(real) once per discriminator step for both the logistic term and the R1 penalty (see
+    Losses.LogisticGAN.shared_real_pass); default from the environment variable SG_SHARED_R1."""
+    from .Losses import LogisticGAN
+    LogisticGAN.shared_real_pass = bool(flag)

@@ -86,6 +86,40 @@ def test_fixed_structure_and_eval_mode():
         g.g_synthesis(torch.zeros(B, arch.num_layers, 512, device=DEV), depth=arch.depth)
 
 
+@pytest.mark.parametrize("res,depth,alpha,fmap_base,fmap_max", [(16, 2, 0.5, 128, 32), (16, 0, 1.0, 128, 32),
+                                                                 (128, 5, 0.3, 512, 32)])
+def test_shared_real_pass_equals_two_pass(res, depth, alpha, fmap_base, fmap_max):
+    """LogisticGAN.dis_loss with one shared D(real) graph for the logistic term and the R1 penalty (the default) against
+    the reference's two-pass formulation (Losses.py:203,214): same loss, same parameter gradients."""
+    import models
+    from models.GAN import Discriminator
+    from models.Losses import LogisticGAN
+    torch.manual_seed(res + depth)
+    d = Discriminator(resolution=res, fmap_base=fmap_base, fmap_max=fmap_max, blur_filter=[1, 2, 1]).to(DEV)
+    with torch.no_grad():
+        for n, p in d.named_parameters():
+            if n.endswith(".bias"):
+                p.copy_(0.1 * torch.randn_like(p))
+    d.train()
+    L = LogisticGAN(d)
+    r = 2 ** (depth + 2)
+    real, fake = torch.randn(4, 3, r, r, device=DEV), torch.randn(4, 3, r, r, device=DEV)
+    params = list(d.parameters())
+    out = []
+    try:
+        for shared in (False, True):
+            models.set_shared_r1(shared)
+            loss = L.dis_loss(real, fake, depth, alpha)
+            out.append((float(loss.detach()), torch.autograd.grad(loss, params, allow_unused=True)))
+    finally:
+        models.set_shared_r1(True)
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert rel(b, a) < 1e-4
+
+
 @pytest.mark.parametrize("loss_name", ["hinge", "relativistic-hinge"])
 def test_other_losses_vs_oracle(loss_name):
     from models import Losses

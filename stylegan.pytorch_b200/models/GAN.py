@@ -426,10 +426,14 @@ class StyleGAN:
                    pad_value=128, padding=1)
 
     def train(self, dataset, num_workers, epochs, batch_sizes, fade_in_percentage, logger, output, num_samples=36,
-              start_depth=0, feedback_factor=100, checkpoint_factor=1):
+              start_depth=0, feedback_factor=100, checkpoint_factor=1, resume=None):
         """Progressive training loop (reference GAN.py:682-826): same schedule, logging lines, sample grids and
-        checkpoint file names.  Under data parallelism only rank 0 writes files."""
+        checkpoint file names.  Additions that leave the reference behaviour untouched when unused: under data
+        parallelism every rank iterates its own shard (`_ddp.sharded_loader`) and only rank 0 writes files; each
+        checkpoint gets an extra `GAN_STATE_<depth>_<epoch>.pth` (`_train_state`), and `resume=` (that file or its
+        dict) continues at the recorded epoch with the recorded fade-in ticker, step count and host RNG."""
         from data import get_data_loader
+        from . import _ddp, _train_state
         assert self.depth <= len(epochs), "epochs not compatible with depth"
         assert self.depth <= len(batch_sizes), "batch_sizes not compatible with depth"
         assert self.depth <= len(fade_in_percentage), "fade_in_percentage not compatible with depth"
@@ -447,15 +451,28 @@ class StyleGAN:
         if self.structure == 'fixed':
             start_depth = self.depth - 1
         step = 1
+        first_epoch, first_ticker = 1, 1
+        if resume is not None:
+            state = _train_state.load(resume)
+            start_depth, first_epoch, first_ticker, step = _train_state.resume_point(state, epochs)
+            _train_state.restore_rng(state, 0 if self.ddp is None else self.ddp.rank)
+            logger.info("Resuming at depth %d, epoch %d, step %d", start_depth + 1, first_epoch, step)
         for current_depth in range(start_depth, self.depth):
             current_res = np.power(2, current_depth + 2)
             logger.info("Currently working on depth: %d", current_depth + 1)
             logger.info("Current resolution: %d x %d" % (current_res, current_res))
-            ticker = 1
-            data = get_data_loader(dataset, batch_sizes[current_depth], num_workers)
-            for epoch in range(1, epochs[current_depth] + 1):
+            resumed_depth = resume is not None and current_depth == start_depth
+            ticker = first_ticker if resumed_depth else 1
+            if self.ddp is None:
+                data = get_data_loader(dataset, batch_sizes[current_depth], num_workers)
+            else:
+                data = _ddp.sharded_loader(dataset, batch_sizes[current_depth], num_workers, self.ddp.rank,
+                                           self.ddp.world)
+            for epoch in range(first_epoch if resumed_depth else 1, epochs[current_depth] + 1):
                 start = timeit.default_timer()
                 logger.info("Epoch: [%d]" % epoch)
+                if self.ddp is not None:
+                    data.sampler.set_epoch(current_depth * 1000 + epoch)
                 total_batches = len(data)
                 fade_point = int((fade_in_percentage[current_depth] / 100) * epochs[current_depth] * total_batches)
                 for i, batch in enumerate(data, 1):
@@ -502,6 +519,8 @@ class StyleGAN:
                         gen_shadow_save_file = os.path.join(save_dir, "GAN_GEN_SHADOW_" + tag)
                         torch.save(self.gen_shadow.state_dict(), gen_shadow_save_file)
                         logger.info("Saving the model to: %s\n" % gen_shadow_save_file)
+                    torch.save(_train_state.capture(current_depth, epoch, ticker, step),
+                               os.path.join(save_dir, "GAN_STATE_" + tag))
         logger.info('Training completed.\n')
 
 

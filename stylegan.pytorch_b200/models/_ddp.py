@@ -73,3 +73,15 @@ class DataParallelContext:
         for p, (b, off) in zip(params, placement):
             p.grad = flats[b][off:off + p.numel()].view_as(p)
         return 1.0 / self.world
+
+
+def sharded_loader(dataset, batch_size, num_workers, rank, world, seed=0):
+    """Per-rank loader for data-parallel training (rank r draws its own local batch): the reference's
+    `data.get_data_loader` settings (`data/__init__.py:32-52`: shuffle, drop_last, pin_memory) with the shuffle moved
+    into a DistributedSampler so that the ranks see disjoint, equally long shards of every epoch.  Call
+    `loader.sampler.set_epoch(e)` before each epoch (StyleGAN.train does)."""
+    from torch.utils.data import DataLoader
+    from torch.utils.data.distributed import DistributedSampler
+    sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True, seed=seed, drop_last=True)
+    return DataLoader(dataset, batch_size=batch_size, sampler=sampler, num_workers=num_workers, drop_last=True,
+                      pin_memory=True)

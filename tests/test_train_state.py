@@ -65,3 +65,85 @@ def test_sharded_loader_partitions_every_epoch():
         assert len(set(flat)) == len(flat)                                           # disjoint shards
         orders.append(seen[0])
     assert orders[0] != orders[1]                                                    # reshuffled per epoch
+
+
+class _Items(torch.utils.data.Dataset):
+    def __init__(self, n):
+        self.x = torch.arange(n).float().view(n, 1, 1, 1).expand(n, 3, 4, 4).contiguous()
+
+    def __len__(self):
+        return len(self.x)
+
+    def __getitem__(self, i):
+        return self.x[i]
+
+
+def _fake_gan(calls):
+    """A StyleGAN whose networks and update steps are stubs: only the control flow of train() is exercised."""
+    import torch.nn as nn
+    from models.GAN import StyleGAN
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = nn.Parameter(torch.zeros(1))
+
+        def forward(self, z, depth, alpha, labels_in=None):
+            return torch.zeros(z.shape[0], 3, 4, 4)
+
+    sg = StyleGAN.__new__(StyleGAN)
+    sg.depth, sg.structure, sg.latent_size, sg.use_ema, sg.conditional = 3, "linear", 8, True, False
+    sg.device, sg.ddp = torch.device("cpu"), None
+    sg.gen, sg.dis, sg.gen_shadow = Net(), Net(), Net()
+    sg.gen_optim = torch.optim.SGD(sg.gen.parameters(), lr=0.1)
+    sg.dis_optim = torch.optim.SGD(sg.dis.parameters(), lr=0.1)
+
+    def d_step(z, img, depth, alpha, labels=None):
+        calls.append(("d", depth, round(float(alpha), 9), round(float(z.sum()), 5), round(float(img.sum()), 3)))
+        return 0.5
+
+    def g_step(z, img, depth, alpha, labels=None):
+        calls.append(("g", depth, round(float(alpha), 9)))
+        return 0.25
+
+    sg.optimize_discriminator, sg.optimize_generator = d_step, g_step
+    sg.create_grid = lambda **kw: None
+    return sg
+
+
+def test_train_loop_resume_continues_the_schedule(tmp_path, monkeypatch):
+    import logging
+    import sys
+    import types
+    stub = types.ModuleType("data")
+
+    def get_data_loader(dataset, batch_size, num_workers):
+        return torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=True, drop_last=True)
+
+    stub.get_data_loader = get_data_loader
+    monkeypatch.setitem(sys.modules, "data", stub)
+    logger = logging.getLogger("test_train_state")
+    kw = dict(dataset=_Items(18), num_workers=0, epochs=[2, 3, 2], batch_sizes=[4, 4, 8], fade_in_percentage=[50, 50, 50],
+              logger=logger, num_samples=4, feedback_factor=2)
+
+    torch.manual_seed(3); random.seed(3); np.random.seed(3)
+    full = []
+    out_a = tmp_path / "a"
+    _fake_gan(full).train(output=str(out_a), **kw)
+    files = sorted(p.name for p in (out_a / "models").iterdir())
+    assert "GAN_GEN_1_2.pth" in files and "GAN_STATE_1_2.pth" in files and "GAN_GEN_SHADOW_2_2.pth" in files
+    assert len([f for f in files if f.startswith("GAN_STATE_")]) == 2 + 3 + 2
+    # alpha ramps from 1/fade_point to 1 over the first half of each depth and stays there
+    d1 = [c for c in full if c[0] == "d" and c[1] == 1]
+    assert len(d1) == 3 * 4 and d1[0][2] == round(1 / 6, 9) and d1[5][2] == 1.0 and d1[-1][2] == 1.0
+
+    # a second process resumes after depth 1, epoch 1 with different ambient RNG: identical remaining calls
+    torch.manual_seed(99); random.seed(99); np.random.seed(99)
+    tail = []
+    _fake_gan(tail).train(output=str(tmp_path / "b"), resume=str(out_a / "models" / "GAN_STATE_1_1.pth"), **kw)
+    first = next(i for i, c in enumerate(full) if c[0] == "d" and c[1] == 1) + 2 * 4      # skip depth 1, epoch 1
+    assert tail == full[first:]
+    # resuming from the last epoch of a depth starts the next depth at alpha = 1 / fade_point
+    tail2 = []
+    _fake_gan(tail2).train(output=str(tmp_path / "c"), resume=str(out_a / "models" / "GAN_STATE_1_3.pth"), **kw)
+    assert tail2 == [c for c in full if c[1] == 2]

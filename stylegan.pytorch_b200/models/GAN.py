@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import Losses, _ops, update_average
+from . import Losses, _host_facade, _ops, update_average
 from ._optim import FusedAdam
 from .Blocks import DiscriminatorBlock, DiscriminatorTop, GSynthesisBlock, InputBlock
 from .CustomLayers import EqualizedConv2d, EqualizedLinear, PixelNormLayer, Truncation, to_nchw, to_nhwc
@@ -60,6 +60,8 @@ class GMapping(nn.Module):
         self.map = nn.Sequential(OrderedDict(layers))
 
     def forward(self, x):
+        if _host_facade.wants_facade(self, x):          # CPU module + CPU latents (generate_* scripts)
+            return _host_facade.call(self, x)
         _ops._require_cuda(x)
         x = x.float()
         for name, m in self.map.named_children():
@@ -113,6 +115,8 @@ class GSynthesis(nn.Module):
     def forward(self, dlatents_in, depth=0, alpha=0., labels_in=None):
         """dlatents_in [B, num_layers, dlatent] -> images [B, C, R, R] float32 (NCHW)."""
         assert depth < self.depth, "Requested output depth cannot be produced"
+        if _host_facade.wants_facade(self, dlatents_in):
+            return _host_facade.call(self, dlatents_in, depth=depth, alpha=alpha, labels_in=labels_in)
         _ops._require_cuda(dlatents_in)
         dl = dlatents_in.float()
         if self.structure == 'fixed':
@@ -162,6 +166,8 @@ class Generator(nn.Module):
             self.truncation = None
 
     def forward(self, latents_in, depth, alpha, labels_in=None):
+        if _host_facade.wants_facade(self, latents_in, labels_in):
+            return _host_facade.call(self, latents_in, depth, alpha, labels_in=labels_in)
         if not self.conditional:
             if labels_in is not None:
                 warnings.warn("Generator is unconditional, labels_in will be ignored")

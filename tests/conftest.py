@@ -14,6 +14,8 @@ sys.dont_write_bytecode = True
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_next: GPU tests of code that has not been run on hardware yet; NOT part of "
+                                       "-m gpu -- run them first in the next GPU session (-m gpu_next), then re-mark")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -26,7 +28,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords:
+        if "gpu" in item.keywords or "gpu_next" in item.keywords:
             item.add_marker(skip)
 
 

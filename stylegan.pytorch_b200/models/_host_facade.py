@@ -15,11 +15,13 @@ _KEY = "_sg_device_replica"
 
 def wants_facade(module, *tensors):
     """True when a CPU-resident module is called with CPU tensors and a GPU exists to run it on."""
-    if not torch.cuda.is_available():
-        return False
-    if any(isinstance(t, torch.Tensor) and t.device.type != "cpu" for t in tensors):
-        return False
-    if not any(isinstance(t, torch.Tensor) for t in tensors):
+    seen = False
+    for t in tensors:                                  # the training step leaves here on its first (CUDA) tensor
+        if isinstance(t, torch.Tensor):
+            if t.device.type != "cpu":
+                return False
+            seen = True
+    if not seen or not torch.cuda.is_available():
         return False
     p = next(module.parameters(), None)
     return p is not None and p.device.type == "cpu"

@@ -275,7 +275,7 @@ def main():
         args.warmup = max(args.warmup, 3)
     verbose = bool(os.environ.get("SG_BENCH_VERBOSE"))
 
-    from models import _lib
+    from models import _lib, Losses
     sg = make_gan(args.res, args.precision, device, seed=1234 + rank)
     depth, alpha, B, R = O_depth(args.res), 0.5, args.batch, args.res
     torch.manual_seed(99 + rank)
@@ -348,14 +348,15 @@ def main():
                "config": {"workload": "StyleGAN G+D step (optimize_discriminator + optimize_generator, logistic + R1, "
                                       "EMA, style mixing, truncation) %dx%d depth %d alpha 0.5" % (R, R, depth),
                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                          "shared_real_pass": True,
+                          "shared_real_pass": bool(Losses.LogisticGAN.shared_real_pass),
                           "l2": "per-step activations (GBs) exceed the 126 MB L2; no explicit flush"},
                "e2e": {"value": round(e2e, 2), "unit": "images/sec", "ms_per_step": round(ms_e2e / args.steps, 3),
                        "h2d_bytes_per_step": B * 3 * R * R * 4 + B * 512 * 4, "d2h_bytes_per_step": 8},
                "gpu_launches": int(launches), "clocks": clocks}
         if fstep:
             out["step_tensor_fraction"] = {"algorithmic_gflop_per_image": fstep,
-                                           "executed_gflop_per_image": F_EXEC_GFLOP.get(R),
+                                           "executed_gflop_per_image": (F_EXEC_GFLOP if Losses.LogisticGAN.shared_real_pass
+                                                                        else F_STEP_GFLOP).get(R),
                                            "achieved_tflops_per_gpu": round(value / world * fstep / 1e3, 1),
                                            "frac_of_sustained_bf16_peak": round(value / world * fstep / 1e3 /
                                                                                 pk["bf16_tflops_sustained"], 4),

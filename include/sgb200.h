@@ -124,6 +124,11 @@ int sg_rgb_out(const void* x, int dtype, const float* W, const float* bias, floa
                float beta, float* out, int N, int h, int w, int C, int K, int up, void* stream);
 int sg_rgb_out_dgrad(const float* g, const float* W, float coef, void* gx, int dtype, int N, int h, int w, int C,
                      int K, int up, void* stream);
+/* Input pipeline: RandomHorizontalFlip + ToTensor + Normalize(0.5, 0.5) of data/transforms.py:11-33 on a uint8 HWC batch
+ * already on the device: in [N,H,W,K] bytes, flip [N] bytes (0/1, may be NULL), out [N,K,H,W] float32, bit-identical to
+ * the CPU transform.  (csrc/sg_input.cu; not yet run on hardware) */
+int sg_image_u8_to_f32(const unsigned char* in, const unsigned char* flip, float* out, int N, int H, int W, int K,
+                       void* stream);
 /* AvgPool2d / nearest interpolate on NCHW float images: GAN.py:382, 575-586 */
 int sg_pool_nchw(const float* in, float* out, long long planes, int Ho, int Wo, int f, float scale, void* stream);
 int sg_upsample_nchw(const float* in, float* out, long long planes, int Hi, int Wi, int f, float scale, void* stream);

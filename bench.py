@@ -133,12 +133,17 @@ def make_gan(res, precision, device, seed):
     sg = StyleGAN(structure="linear", resolution=res, num_channels=3, latent_size=512, g_args=g_args, d_args=d_args,
                   g_opt_args=opt, d_opt_args=dict(opt), loss="logistic", use_ema=True, ema_decay=0.999, device=device)
     sg.gen.train(); sg.dis.train(); sg.gen_shadow.train()
-    # the reference initialises noise weights to zero (CustomLayers.py:188); randomise so the noise path does work
+    # the reference initialises noise weights to zero (CustomLayers.py:188); randomise so the noise path does work.
+    # Drawn from a rank-independent CPU generator so that data-parallel replicas stay identical after the rank-0
+    # broadcast StyleGAN.__init__ has already done.
+    gen = torch.Generator().manual_seed(4321)
     with torch.no_grad():
         for n, p in sg.gen.named_parameters():
             if n.endswith("noise.weight"):
-                p.copy_(torch.randn_like(p))
+                p.copy_(torch.randn(p.shape, generator=gen).to(p.device))
         sg.gen_shadow.load_state_dict(sg.gen.state_dict())
+    from models import _ops
+    _ops.clear_weight_cache()
     return sg
 
 
@@ -179,9 +184,21 @@ def northstar_kernel_roofline(batch, res, ch, iters=20):
             "peak_source": how + " (burst cuBLAS bf16; kernel timed alone)", "ms_per_launch": round(ms, 4),
             "algorithmic_gflop_per_launch": round(flops / 1e9, 1),
             "hbm_gbs_algorithmic": round(alg_bytes / (ms * 1e-3) / 1e9, 1),
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
-            # (profiles/r01_summary.md); the algorithmic minimum is 537 MB
-            "traffic": 487.7e6 if (batch, res, ch) == (32, 256, 64) else None, "traffic_unit": "bytes/launch"}
+            **northstar_traffic(batch, res, ch)}
+
+
+def northstar_traffic(batch, res, ch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the north-star kernel from the committed
+    `ncu --set full` capture (profiles/northstar_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep);
+    null when no capture exists for this shape."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "northstar_traffic.json")))
+        for r in rec["captures"]:
+            if (r["batch"], r["res"], r["ch"]) == (batch, res, ch):
+                return {"traffic": r["dram_bytes"], "traffic_unit": "bytes/launch", "traffic_source": r["source"]}
+    except Exception:
+        pass
+    return {"traffic": None, "traffic_unit": "bytes/launch", "traffic_source": None}
 
 
 def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):
@@ -190,8 +207,8 @@ def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import stylegan_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    # torch.distributed.run exports OMP_NUM_THREADS=1: the CPU arm must still use every host core
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(0); random.seed(0)
     arch = O.Arch(res)
     gen = torch.Generator().manual_seed(0)
@@ -210,6 +227,117 @@ def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):
         if i >= warmup:
             times.append(dt)
     return times, torch.get_num_threads()
+
+
+def gpu_oracle_step_time(res, batch, steps, warmup, mode):
+    """The honest GPU comparator: the SAME eager-PyTorch formulation the reference executes (the oracle
+    port = the reference's functions on flat state dicts), run on this B200 through cuDNN / cuBLAS instead of our
+    kernels.  mode 'fp32': plain fp32 with cudnn.benchmark=True (reference train.py:77); mode 'bf16': the same under
+    torch.autocast(bfloat16) with channels_last inputs and weights.  None of this library's kernels run here.
+    -> ms/step (CUDA events)."""
+    import random
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stylegan_oracle as O
+    dev = torch.device("cuda")
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0); random.seed(0)
+    arch = O.Arch(res)
+    gen = torch.Generator().manual_seed(0)
+    g_sd = {k: v.to(dev) for k, v in O.init_generator(arch, gen).items()}
+    d_sd = {k: v.to(dev) for k, v in O.init_discriminator(arch, gen).items()}
+    cl = mode == "bf16"
+    if cl:
+        for sd in (g_sd, d_sd):
+            for k, v in sd.items():
+                if v.dim() == 4:
+                    sd[k] = v.contiguous(memory_format=torch.channels_last)
+    st = O.TrainState(arch, g_sd, d_sd)
+    depth = arch.depth - 1
+    ev = []
+    for i in range(warmup + steps):
+        real = torch.randn(batch, 3, res, res, device=dev)
+        if cl:
+            real = real.contiguous(memory_format=torch.channels_last)
+        z = torch.randn(batch, 512, device=dev)
+        nd = [torch.randn(s, device=dev) for s in O.noise_shapes(arch, batch, depth)]
+        ng = [torch.randn(s, device=dev) for s in O.noise_shapes(arch, batch, depth)]
+        md, mg = O.draw_mixing(arch, z.shape, depth), O.draw_mixing(arch, z.shape, depth)
+        md, mg = (md[0].to(dev), md[1]), (mg[0].to(dev), mg[1])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if cl:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                O.train_step(st, real, z, depth, 0.5, md, mg, nd, ng)
+        else:
+            O.train_step(st, real, z, depth, 0.5, md, mg, nd, ng)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ev.append(e0.elapsed_time(e1))
+    del st, g_sd, d_sd
+    torch.cuda.empty_cache()
+    return sum(ev) / len(ev)
+
+
+def dp_self_check(sg, device, world, rank, depth, alpha, B, R):
+    """Data-parallel invariants, checked on the NCCL path before timing:
+      (1) the all-reduced gradients equal the mean of the per-rank gradients (gathered and averaged independently);
+      (2) after two optimizer steps every rank holds bit-identical G, D and shadow parameters and avg_latent.
+    -> "ok" or a description of the first violation (same string on every rank)."""
+    import torch
+    import torch.distributed as dist
+
+    def digest(mods):
+        acc = []
+        for m in mods:
+            for t in list(m.parameters()) + list(m.buffers()):
+                acc.append(t.detach().double().sum().reshape(1))
+                acc.append((t.detach().double() * 1.000001).abs().sum().reshape(1))
+        return torch.cat(acc)
+
+    msg = "ok"
+    # (1) gradient averaging: run a D backward by hand, keep the local grads, then let the exchange run
+    torch.manual_seed(7 + rank)
+    img = torch.randn(B, 3, R, R, device=device)
+    z = torch.randn(B, 512, device=device)
+    with torch.no_grad():
+        fake = sg.gen(z, depth, alpha).detach()
+        real = sg._StyleGAN__progressive_down_sampling(img, depth, alpha)
+    loss = sg.loss.dis_loss(real, fake, depth, alpha)
+    sg.dis_optim.zero_grad()
+    loss.backward()
+    params = [p for p in sg.dis.parameters() if p.grad is not None]
+    local = torch.cat([p.grad.detach().reshape(-1).float() for p in params])
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean = torch.stack(gathered).double().mean(0)
+    scale = sg.ddp.allreduce_grads(sg.dis_optim)
+    got = torch.cat([p.grad.detach().reshape(-1).double() for p in params]) * scale
+    err = float((got - mean).norm() / (mean.norm() + 1e-30))
+    if not err < 1e-5:
+        msg = "allreduce != mean of rank grads (rel %.3e)" % err
+    sg.dis_optim.zero_grad()
+    # (2) replicas identical after two full steps on rank-specific data
+    for i in range(2):
+        img = torch.randn(B, 3, R, R, device=device)
+        z = torch.randn(B, 512, device=device)
+        sg.optimize_discriminator(z, img, depth, alpha)
+        sg.optimize_generator(z, img, depth, alpha)
+    d = digest([sg.gen, sg.dis, sg.gen_shadow])
+    all_d = [torch.empty_like(d) for _ in range(world)]
+    dist.all_gather(all_d, d)
+    for r in range(1, world):
+        if not torch.equal(all_d[0], all_d[r]):
+            bad = int((all_d[0] != all_d[r]).nonzero()[0])
+            if msg == "ok":
+                msg = "replica %d differs from replica 0 after 2 steps (digest entry %d)" % (r, bad)
+            break
+    flag = torch.tensor([0 if msg == "ok" else 1], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag) and msg == "ok":
+        msg = "violation seen on another rank"
+    return msg
 
 
 def run_reference(args, rank, world):
@@ -254,6 +382,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -319,6 +448,10 @@ def main():
         return float(ms)
 
     import gc
+    dp_check = None
+    if world > 1:
+        dp_check = dp_self_check(sg, device, world, rank, depth, alpha, B, R)
+        torch.manual_seed(99 + rank)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                    # spawned before the warm-up so that its start-up cost is not in the timing
@@ -353,24 +486,49 @@ def main():
                "e2e": {"value": round(e2e, 2), "unit": "images/sec", "ms_per_step": round(ms_e2e / args.steps, 3),
                        "h2d_bytes_per_step": B * 3 * R * R * 4 + B * 512 * 4, "d2h_bytes_per_step": 8},
                "gpu_launches": int(launches), "clocks": clocks}
+        if dp_check is not None:
+            out["dp_check"] = dp_check
         if fstep:
-            out["step_tensor_fraction"] = {"algorithmic_gflop_per_image": fstep,
-                                           "executed_gflop_per_image": (F_EXEC_GFLOP if Losses.LogisticGAN.shared_real_pass
-                                                                        else F_STEP_GFLOP).get(R),
-                                           "achieved_tflops_per_gpu": round(value / world * fstep / 1e3, 1),
-                                           "frac_of_sustained_bf16_peak": round(value / world * fstep / 1e3 /
-                                                                                pk["bf16_tflops_sustained"], 4),
-                                           "peak_source": how}
+            fexec = (F_EXEC_GFLOP if Losses.LogisticGAN.shared_real_pass else F_STEP_GFLOP).get(R)
+            out["step_tensor_fraction"] = {
+                # EXECUTED FLOPs (4 F_G + 11 F_D with the shared D(real) graph) are what the fraction is computed from
+                "executed_gflop_per_image": fexec,
+                "achieved_tflops_per_gpu": round(value / world * fexec / 1e3, 1),
+                "frac_of_sustained_bf16_peak": round(value / world * fexec / 1e3 / pk["bf16_tflops_sustained"], 4),
+                # the reference formulation's count (4 F_G + 14 F_D) for comparison only
+                "reference_formulation_gflop_per_image": fstep,
+                "reference_equivalent_tflops_per_gpu": round(value / world * fstep / 1e3, 1),
+                "peak_source": how}
         ch = {128: 128, 256: 64, 512: 32, 1024: 16}.get(R, 64)
         try:
             out["roofline"] = northstar_kernel_roofline(B, R, ch) if args.precision == "bf16" else None
         except Exception as e:                              # the roofline probe must never lose the headline number
             out["roofline"] = {"error": str(e)[:200]}
+        if world == 1 and not args.no_gpu_baseline:
+            # honest GPU comparator: eager PyTorch + cuDNN/cuBLAS on this same B200, same step, same batch
+            gb = {"unit": "images/sec", "batch": B, "what": "oracle port of the reference step, eager PyTorch on this "
+                  "GPU (cuDNN/cuBLAS; none of this library's kernels)", "timing": "1 warm-up + 3 timed steps, CUDA events"}
+            del sg
+            gc.collect(); torch.cuda.empty_cache()
+            for mode in ("bf16", "fp32"):
+                try:
+                    msb = gpu_oracle_step_time(R, B, 3, 1, mode)
+                    gb[mode] = {"value": round(B / (msb * 1e-3), 2), "ms_per_step": round(msb, 2),
+                                "how": "autocast(bfloat16) + channels_last" if mode == "bf16"
+                                       else "fp32, cudnn.benchmark=True (reference train.py:77)"}
+                except Exception as e:
+                    gb[mode] = {"error": str(e)[:160]}
+            best = max((gb[m].get("value", 0.0) for m in ("bf16", "fp32")), default=0.0)
+            gb["speedup_vs_best"] = round(value / best, 2) if best else None
+            out["gpu_baseline"] = gb
         if world == 1 and not args.no_cpu_baseline:
-            t, threads = cpu_oracle_step_time(R, args.ref_batch, 1, 0)
-            out["cpu_baseline"] = {"value": round(args.ref_batch / t[0], 4), "unit": "images/sec", "cores": threads,
-                                   "kind": "port", "sample": "1 G+D step at %dx%d, batch %d, oracle port on host CPU"
-                                                              % (R, R, args.ref_batch)}
+            cb = 1                                          # ~10 s of CPU per image at 256x256: 1 warm-up + 3 timed steps
+            t, threads = cpu_oracle_step_time(R, cb, 3, 1)
+            out["cpu_baseline"] = {"value": round(cb * len(t) / sum(t), 4), "unit": "images/sec", "cores": threads,
+                                   "kind": "port", "sample": "1 warm-up + 3 timed G+D steps at %dx%d, batch %d (the "
+                                   "per-image cost of this path does not depend on the batch), oracle port on the "
+                                   "host CPU, all %d threads" % (R, R, cb, threads),
+                                   "sec_per_step": [round(x, 2) for x in t]}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -42,6 +42,9 @@ const char* sg_last_error(void);
 int sg_abi_version(void);
 int sg_geom_size(void);
 int sg_entry_size(void);
+/* 1 (default): shape-specialised kernels where they apply (4-pixel blur strips, K=3 to/from-RGB, one-row weighted
+ * channel sums); 0: general kernels only; <0: query.  Returns the previous setting.  Same results either way. */
+int sg_fast_paths(int enable);
 
 /* ---- dense convolutions: EqualizedConv2d.forward, models/CustomLayers.py:137-180 (F.conv2d :163,:171,:173,
  *      F.conv_transpose2d :151) and their autograd adjoints ------------------------------------------------------- */

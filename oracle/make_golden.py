@@ -195,6 +195,82 @@ def golden_other_losses(name, arch, batch, depth, alpha, seed=3):
           {k: (round(v["d_loss"], 5), round(v["g_loss"], 5)) for k, v in fx["losses"].items()})
 
 
+class _FixedMixing:
+    """Make the reference's next training-mode Generator.forward draw (z2, cutoff) (GAN.py:282-290)."""
+
+    def __init__(self, z2, cutoff):
+        self.z2, self.cutoff = z2, cutoff
+
+    def __enter__(self):
+        self._randn, self._random, self._randint = torch.randn, random.random, random.randint
+        z2, me = self.z2, self
+
+        def fake_randn(*a, **k):
+            torch.randn = me._randn
+            return z2.clone()
+        torch.randn = fake_randn
+        random.random = lambda: 0.0
+        random.randint = lambda a, b: self.cutoff
+
+    def __exit__(self, *a):
+        torch.randn, random.random, random.randint = self._randn, self._random, self._randint
+
+
+def golden_full_width(name, res, batch, seed, alpha=0.5):
+    """BASELINE configs 2/3 at the reference's REAL channel widths, top depth, small batch: the inputs are
+    O.seeded_case(arch, batch, depth, seed) (re-derivable, not stored); stored are the reference's outputs: the image
+    at the top depth (alpha) and at every lower depth (alpha 1), both logit vectors, R1, both losses, and for every
+    parameter gradient its norm and a 64-value head (full tensor when <= 4096 elements)."""
+    arch = O.Arch(res)
+    depth = arch.depth - 1
+    case = O.seeded_case(arch, batch, depth, seed)
+    seed_all(seed)
+    sg = build_reference(arch)
+    sg.gen.load_state_dict(case["g_sd"]); sg.dis.load_state_dict(case["d_sd"])
+    sg.gen.train(); sg.dis.train()
+    layers = [m for m in sg.gen.g_synthesis.modules() if isinstance(m, NoiseLayer)]
+    for m, n in zip(layers, case["noises"]):
+        m.noise = n
+    z, real = case["z"], case["real"]
+    lower = {}
+    with torch.no_grad():
+        for d_ in range(depth):
+            # the truncation average must not drift between these probes: restore it each time
+            avg0 = sg.gen.truncation.avg_latent.clone()
+            with _FixedMixing(case["z2"], min(case["cutoff"], 2 * (d_ + 1))):
+                lower[d_] = sg.gen(z, d_, 1.0).clone()
+            sg.gen.truncation.avg_latent.copy_(avg0)
+    with _FixedMixing(case["z2"], case["cutoff"]):
+        fake = sg.gen(z, depth, alpha)
+    avg_after = sg.gen.truncation.avg_latent.clone()
+    logits_fake = sg.dis(fake, depth, alpha)
+    logits_real = sg.dis(real, depth, alpha)
+    r1 = sg.loss.R1Penalty(real, depth, alpha)
+    d_loss = sg.loss.dis_loss(real, fake.detach(), depth, alpha)
+    d_grads = torch.autograd.grad(d_loss, list(sg.dis.parameters()), allow_unused=True)
+    g_loss = sg.loss.gen_loss(None, fake, depth, alpha)
+    g_grads = torch.autograd.grad(g_loss, list(sg.gen.parameters()), allow_unused=True)
+    gn = [n for n, _ in sg.gen.named_parameters()]
+    dn = [n for n, _ in sg.dis.named_parameters()]
+
+    def pack(names, grads):
+        out = {}
+        for n, g in zip(names, grads):
+            if g is None:
+                continue
+            out[n] = dict(norm=float(g.norm()), full=g.clone() if g.numel() <= 4096 else None,
+                          head=g.flatten()[:64].clone())
+        return out
+    fx = dict(arch=arch.__dict__.copy(), res=res, batch=batch, depth=depth, alpha=alpha, seed=seed,
+              fake=fake.detach().clone(), lower=lower, avg_after=avg_after, logits_fake=logits_fake.detach().clone(),
+              logits_real=logits_real.detach().clone(), r1=float(r1), d_loss=float(d_loss), g_loss=float(g_loss),
+              d_grads=pack(dn, d_grads), g_grads=pack(gn, g_grads))
+    out = os.path.join(ROOT, "tests", "golden", name + ".pt")
+    torch.save(fx, out)
+    print(name, "->", out, "%.1f KB" % (os.path.getsize(out) / 1024), "d_loss %.5f g_loss %.5f r1 %.5f" %
+          (fx["d_loss"], fx["g_loss"], fx["r1"]))
+
+
 def live_full_width(outdir):
     """BASELINE config 1 at the reference's real channel widths (too large to commit): resolution-128 config,
     depth 1 (8x8) and depth 2 (16x16), batch 4.  Used by tests/test_oracle_vs_reference.py in the build container."""
@@ -204,6 +280,11 @@ def live_full_width(outdir):
 
 
 def main():
+    if len(sys.argv) >= 2 and sys.argv[1] == "--full":
+        # BASELINE configs 2 and 3 at full width (minutes of CPU): python oracle/make_golden.py --full
+        golden_full_width("full128_d5", 128, batch=4, seed=11)
+        golden_full_width("full256_d6", 256, batch=4, seed=12)
+        return
     if len(sys.argv) >= 3 and sys.argv[1] == "--live":
         os.makedirs(sys.argv[2], exist_ok=True)
         return live_full_width(sys.argv[2])

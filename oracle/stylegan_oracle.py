@@ -134,7 +134,7 @@ def eq_conv(x: Tensor, w: Tensor, b: Optional[Tensor], gain: float) -> Tensor:
 def blur3(x: Tensor) -> Tensor:
     """Depthwise [1,2,1]x[1,2,1]/16, pad 1.  models/CustomLayers.py:251-276."""
     c = x.shape[1]
-    k1 = torch.tensor([1.0, 2.0, 1.0], dtype=x.dtype)
+    k1 = torch.tensor([1.0, 2.0, 1.0], dtype=x.dtype, device=x.device)
     k = (k1[:, None] * k1[None, :]) / 16.0
     return F.conv2d(x, k[None, None].expand(c, 1, 3, 3), padding=1, groups=c)
 
@@ -290,7 +290,7 @@ def g_synthesis(sd: SD, dlatents: Tensor, depth: int, alpha: float, arch: Arch,
 def truncate(dlatents: Tensor, avg: Tensor, psi: float, cutoff: int) -> Tensor:
     """models/CustomLayers.py:319-323."""
     interp = torch.lerp(avg, dlatents, psi)
-    mask = (torch.arange(dlatents.shape[1]) < cutoff).view(1, -1, 1)
+    mask = (torch.arange(dlatents.shape[1], device=dlatents.device) < cutoff).view(1, -1, 1)
     return torch.where(mask, interp, dlatents)
 
 
@@ -312,7 +312,7 @@ def generator_forward(sd: SD, z: Tensor, depth: int, alpha: float, arch: Arch, *
             assert z2 is not None and mixing_cutoff is not None
             w2 = g_mapping(sd, z2, arch)
             dl2 = w2.unsqueeze(1).expand(-1, arch.num_layers, -1)
-            layer_idx = torch.arange(arch.num_layers).view(1, -1, 1)
+            layer_idx = torch.arange(arch.num_layers, device=dl.device).view(1, -1, 1)
             dl = torch.where(layer_idx < mixing_cutoff, dl, dl2)                                       # GAN.py:289
         if has_trunc:
             dl = truncate(dl, sd["truncation.avg_latent"], arch.truncation_psi, arch.truncation_cutoff)
@@ -629,3 +629,30 @@ def init_discriminator(arch: Arch, gen: Optional[torch.Generator] = None) -> SD:
         sd[f"from_rgb.{j}.weight"] = rn(cj, arch.num_channels, 1, 1)
         sd[f"from_rgb.{j}.bias"] = torch.zeros(cj)
     return sd
+
+
+# --------------------------------------------------------------------------- #
+# seeded full-width cases (fixtures too large to commit are re-derived from a seed)
+# --------------------------------------------------------------------------- #
+def seeded_case(arch: Arch, batch: int, depth: int, seed: int) -> dict:
+    """Every INPUT of a full-width forward/backward fixture, derived from one CPU generator seed: initial state
+    dicts (reference distributions; noise weights ~N(0,1) and biases ~0.1 N(0,1) so those paths carry signal,
+    SURVEY 8(d)), per-layer noise, latents, second latents + mixing cut-off, real images.  oracle/make_golden.py
+    feeds exactly this to the live reference and commits only the OUTPUTS; the tests rebuild the inputs on the GPU box
+    with the same call (torch's CPU Philox/MT stream is a function of the seed and the torch build, which is the
+    same image on both sides)."""
+    gen = torch.Generator().manual_seed(seed)
+    g_sd, d_sd = init_generator(arch, gen), init_discriminator(arch, gen)
+    for sd in (g_sd, d_sd):
+        for k in sd:
+            if k.endswith("noise.weight"):
+                sd[k] = torch.randn(sd[k].shape, generator=gen)
+            elif k.endswith(".bias") and "init_block.bias" not in k:
+                sd[k] = 0.1 * torch.randn(sd[k].shape, generator=gen)
+    noises = [torch.randn(s, generator=gen) for s in noise_shapes(arch, batch, depth)]
+    z = torch.randn(batch, arch.latent_size, generator=gen)
+    z2 = torch.randn(batch, arch.latent_size, generator=gen)
+    cutoff = int(torch.randint(1, 2 * (depth + 1) + 1, (1,), generator=gen))
+    res = 2 ** (depth + 2)
+    real = torch.randn(batch, arch.num_channels, res, res, generator=gen)
+    return dict(g_sd=g_sd, d_sd=d_sd, noises=noises, z=z, z2=z2, cutoff=cutoff, real=real)

@@ -1,12 +1,12 @@
-// NEXT-ROUND CANDIDATE, not part of libsgb200.so and not yet run on hardware (built by tools/build_next.py into
-// lib/libsgb200_next.so, exercised by tests/test_next_kernels.py [gpu_next] and tools/bench_next.py).
+// Fast path of sg_blur3 (BlurLayer, reference models/CustomLayers.py:266-276): measured 4.93 TB/s against 3.08 TB/s
+// for the general strip kernel at 32x256x256x64 bf16 (profiles/r02_pointwise_microbench.txt).
 //
-// blur3 v2: the product kernel (csrc/sg_pointwise.cu) is issue-bound at ~206 instructions per 16-byte output vector
-// (3.2 TB/s).  Here a thread owns FOUR adjacent pixels of one 16-byte channel vector and an 8-row strip: per input row
+// blur3 v2: the general kernel (csrc/sg_pointwise.cu) is issue-bound at ~206 instructions per 16-byte output vector.  Here a thread owns FOUR adjacent pixels of one 16-byte channel vector and an 8-row strip: per input row
 // it unpacks 6 neighbour vectors for 4 outputs (1.5 instead of 3 per output), border columns are zeroed on the packed
 // words of the two edge vectors only, and only the first / last row of a strip can be outside the image.
 // Static count: ~75 instructions per output vector.  Requires W % 4 == 0, H % 8 == 0, C % (16 / sizeof(T)) == 0.
-#include "../csrc/sg_common.cuh"
+#include "sg_common.cuh"
+#include "sg_fast.cuh"
 
 namespace {
 
@@ -114,25 +114,25 @@ __global__ void __launch_bounds__(128, 3) blur3_v2_kernel(const T* __restrict__ 
 
 }  // namespace
 
-extern "C" __attribute__((visibility("default")))
-int sgn_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W, int C,
+// -> 0 launched, SG_FAST_UNSUPPORTED when the shape is outside this kernel's domain (caller falls back), else cudaError
+int sgf_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W, int C,
               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (H % STRIP != 0 || W % PX != 0) return 1000;
+  if (H % STRIP != 0 || W % PX != 0) return SG_FAST_UNSUPPORTED;
   if (dtype == SG_BF16) {
     using T = __nv_bfloat16;
-    if (C % SgVec<T>::N != 0) return 1000;
+    if (C % SgVec<T>::N != 0) return SG_FAST_UNSUPPORTED;
     long long total = (long long)N * (H / STRIP) * (W / PX) * (C / SgVec<T>::N);
-    if (total >= (1ll << 30)) return 1000;
+    if (total >= (1ll << 30)) return SG_FAST_UNSUPPORTED;
     blur3_v2_kernel<T><<<sg_grid_1d(total, 128, 148 * 16), 128, 0, st>>>((const T*)x, (T*)y, bias, bias_mul, N, H, W, C);
   } else if (dtype == SG_F32) {
     using T = float;
-    if (C % SgVec<T>::N != 0) return 1000;
+    if (C % SgVec<T>::N != 0) return SG_FAST_UNSUPPORTED;
     long long total = (long long)N * (H / STRIP) * (W / PX) * (C / SgVec<T>::N);
-    if (total >= (1ll << 30)) return 1000;
+    if (total >= (1ll << 30)) return SG_FAST_UNSUPPORTED;
     blur3_v2_kernel<T><<<sg_grid_1d(total, 128, 148 * 16), 128, 0, st>>>((const T*)x, (T*)y, bias, bias_mul, N, H, W, C);
   } else {
-    return 1001;
+    return SG_FAST_UNSUPPORTED;
   }
   return (int)cudaGetLastError();
 }

@@ -1,0 +1,15 @@
+// Internal fast paths behind the C-ABI entry points of sg_pointwise.cu (not exported).  Each returns 0 when it has
+// launched, SG_FAST_UNSUPPORTED when the shape is outside its domain (the entry point then runs the general kernel),
+// or a cudaError_t.  sg_fast_paths(0) (C-ABI) switches them off so that tests can compare both implementations.
+#pragma once
+#define SG_FAST_UNSUPPORTED 1000
+extern int g_sg_fast_paths;
+int sgf_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W, int C,
+              void* stream);
+int sgf_rgb_in3(const float* img, const float* W, const float* bias, float scale, float bias_mul, int act, void* y,
+                int N, int HW, int C, void* stream);
+int sgf_rgb_out3(const void* x, const float* W, const float* bias, float scale, float bias_mul, float alpha, float beta,
+                 float* out, int N, int h, int w, int C, int up, void* stream);
+int sgf_channel_sum_blocks(long long P);
+int sgf_channel_sum_w1(const void* x, const float* wt, long long P, int C, float* ws, float* out, float scale,
+                       void* stream);

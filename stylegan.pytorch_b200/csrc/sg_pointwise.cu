@@ -1,6 +1,7 @@
 // Bandwidth-bound NHWC kernels: blur, axpby/lerp, LeakyReLU backward, casts, per-channel reductions, from/to-RGB
 // pointwise convolutions (NCHW fp32 image side <-> NHWC feature side), image pooling, dlatent assembly.
 #include "sg_common.cuh"
+#include "sg_fast.cuh"
 #include "../../include/sgb200.h"
 
 namespace {
@@ -848,6 +849,10 @@ SG_EXPORT int sg_bias_noise(const void* x, const float* bias, float bias_mul, co
 SG_EXPORT int sg_blur3(const void* x, void* y, const float* bias, float bias_mul, int dtype, int N, int H, int W,
                        int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sg_fast_paths) {
+    int rc = sgf_blur3(x, y, bias, bias_mul, dtype, N, H, W, C, stream);
+    if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_blur3/v2: launch failed"); return rc; }
+  }
   SG_DISPATCH(dtype, {
     if (C % SgVec<T>::N == 0) {
       long long total = (long long)N * ((H + BLUR_STRIP - 1) / BLUR_STRIP) * W * (C / SgVec<T>::N);
@@ -905,6 +910,11 @@ SG_EXPORT int sg_channel_sum(const void* x, int dtype, const float* wt, int J, i
   SG_REQUIRE(rows >= 1 && rows <= CS_ROWS && J >= 0, "sg_channel_sum: rows must be 1..4");
   SG_REQUIRE(J == 0 || wt != nullptr, "sg_channel_sum: weights missing");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sg_fast_paths && dtype == SG_BF16 && J == 1 && ones && !accumulate) {
+    // noise-weight + bias gradient: one per-pixel weight row plus the plain sum (same workspace layout and blocks)
+    int rc = sgf_channel_sum_w1(x, wt, P, C, part_ws, out, scale, stream);
+    if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_channel_sum/w1: launch failed"); return rc; }
+  }
   int nblk = sg_channel_sum_blocks(P);
   int pix_per_blk = (int)((P + nblk - 1) / nblk);
   int bx = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
@@ -937,6 +947,10 @@ SG_EXPORT int sg_rgb_in(const float* img, const float* W, const float* bias, flo
                         void* y, int dtype, int N, int HW, int K, int C, void* stream) {
   SG_REQUIRE(K >= 1 && K <= 4, "sg_rgb_in: K must be 1..4");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sg_fast_paths && dtype == SG_BF16 && K == 3) {
+    int rc = sgf_rgb_in3(img, W, bias, scale, bias_mul, act, y, N, HW, C, stream);
+    if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_rgb_in/k3: launch failed"); return rc; }
+  }
   long long total = (long long)N * HW * C;
   SG_DISPATCH(dtype, {
     if (C % SgVec<T>::N == 0 && 256 % (C / SgVec<T>::N) == 0 && total / SgVec<T>::N < (1ll << 30))   // CV | 256 -> fixed cv per thread
@@ -967,6 +981,10 @@ SG_EXPORT int sg_rgb_out(const void* x, int dtype, const float* W, const float* 
                          float alpha, float beta, float* out, int N, int h, int w, int C, int K, int up, void* stream) {
   SG_REQUIRE(K >= 1 && K <= 4 && up >= 1 && up <= 2, "sg_rgb_out: K must be 1..4, up 1..2");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sg_fast_paths && dtype == SG_BF16 && K == 3) {
+    int rc = sgf_rgb_out3(x, W, bias, scale, bias_mul, alpha, beta, out, N, h, w, C, up, stream);
+    if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_rgb_out/k3: launch failed"); return rc; }
+  }
   long long P = (long long)N * h * w;
   SG_DISPATCH(dtype, {
     SG_REQUIRE(C % SgVec<T>::N == 0, "sg_rgb_out: C must be a multiple of the 16-byte vector width");

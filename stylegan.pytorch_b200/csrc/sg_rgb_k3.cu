@@ -1,10 +1,14 @@
-// NEXT-ROUND CANDIDATES, not part of libsgb200.so and not yet run on hardware (see sgn_blur.cu).
+// Fast paths of sg_rgb_in / sg_rgb_out / sg_channel_sum for the StyleGAN case K = 3, bf16 activations (from_rgb / to_rgb,
+// reference models/GAN.py:157,167,358,377; noise-weight + bias gradient sums).  Measured against the general kernels at
+// 32x256x256x64 (profiles/r02_pointwise_microbench.txt): rgb_in 2.05 -> 2.55 TB/s, rgb_out 1.00 -> 2.46 TB/s,
+// weighted channel sum 2.16 -> 3.69 TB/s.
 //
-// The product to/from-RGB kernels are issue-bound (profiles/r01_summary.md): rgb_out spends ~1100 of its ~2200
+// The general to/from-RGB kernels are issue-bound (profiles/r01_summary.md): rgb_out spends ~1100 of its ~2200
 // instructions per 16 pixels in the (k, a, b) scatter (four runtime divisions and 64-bit address arithmetic per lane),
 // rgb_in_vec ~150 per output vector (two divisions, K padded to 4, select-based LeakyReLU).  Versions with K = 3 fixed at
 // compile time, the per-lane scatter offsets hoisted out of the pixel loop and no division in the steady state.
-#include "../csrc/sg_common.cuh"
+#include "sg_common.cuh"
+#include "sg_fast.cuh"
 
 namespace {
 
@@ -201,13 +205,13 @@ __global__ void __launch_bounds__(128) reduce_parts_kernel(const float* __restri
 
 }  // namespace
 
-#define SGN_EXPORT extern "C" __attribute__((visibility("default")))
+#define SGN_EXPORT
 
 // from_rgb (bf16 output, K = 3).  Returns 1000 when the shape is outside this kernel's fast path.
-SGN_EXPORT int sgn_rgb_in3(const float* img, const float* W, const float* bias, float scale, float bias_mul, int act,
+SGN_EXPORT int sgf_rgb_in3(const float* img, const float* W, const float* bias, float scale, float bias_mul, int act,
                            void* y, int N, int HW, int C, void* stream) {
   const int CV = C / 8;
-  if (C % 8 != 0 || CV < 1 || 256 % CV != 0 || (long long)N * HW * CV >= (1ll << 30)) return 1000;
+  if (C % 8 != 0 || CV < 1 || 256 % CV != 0 || (long long)N * HW * CV >= (1ll << 30)) return SG_FAST_UNSUPPORTED;
   const long long total = (long long)N * HW * CV;
   const int grid = sg_grid_1d(total, 256, 148 * 8);
   cudaStream_t st = (cudaStream_t)stream;
@@ -217,16 +221,16 @@ SGN_EXPORT int sgn_rgb_in3(const float* img, const float* W, const float* bias, 
 }
 
 // to_rgb (bf16 input, K = 3, up 1 or 2).
-SGN_EXPORT int sgn_rgb_out3(const void* x, const float* W, const float* bias, float scale, float bias_mul, float alpha,
+SGN_EXPORT int sgf_rgb_out3(const void* x, const float* W, const float* bias, float scale, float bias_mul, float alpha,
                             float beta, float* out, int N, int h, int w, int C, int up, void* stream) {
-  if (C % 8 != 0 || up < 1 || up > 2) return 1000;
+  if (C % 8 != 0 || up < 1 || up > 2) return SG_FAST_UNSUPPORTED;
   const int CV = C / 8;
   int G = 1;
   while (G < CV || G < 3 * up * up) G <<= 1;               // one lane per channel vector, and 3*up*up writer lanes
-  if (G > 32) return 1000;
+  if (G > 32) return SG_FAST_UNSUPPORTED;
   constexpr int U = 4;
   const int span = (32 / G) * U;
-  if (w % span != 0 || (long long)N * h * w >= (1ll << 30)) return 1000;
+  if (w % span != 0 || (long long)N * h * w >= (1ll << 30)) return SG_FAST_UNSUPPORTED;
   const long long iters = (long long)N * h * w / span;
   const int grid = sg_grid_1d(iters * 32, 256, 148 * 8);
   rgb_out3_kernel<U><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, W, bias, scale, bias_mul, alpha,
@@ -235,17 +239,17 @@ SGN_EXPORT int sgn_rgb_out3(const void* x, const float* W, const float* bias, fl
 }
 
 // out[0][c] = scale * sum_p wt[p] x[p][c], out[1][c] = scale * sum_p x[p][c]; ws: nblk*2*C floats (nblk = return of
-// sgn_channel_sum_blocks).
-SGN_EXPORT int sgn_channel_sum_blocks(long long P) {
+// sgf_channel_sum_blocks).
+SGN_EXPORT int sgf_channel_sum_blocks(long long P) {
   long long b = (P + 255) / 256;
   if (b > 148 * 4) b = 148 * 4;
   return b < 1 ? 1 : (int)b;
 }
-SGN_EXPORT int sgn_channel_sum_w1(const void* x, const float* wt, long long P, int C, float* ws, float* out, float scale,
+SGN_EXPORT int sgf_channel_sum_w1(const void* x, const float* wt, long long P, int C, float* ws, float* out, float scale,
                                   void* stream) {
   const int CV = C / 8;
-  if (C % 8 != 0 || CV > 256 || (size_t)2 * (256 / CV) * C * sizeof(float) > 48 * 1024) return 1000;
-  const int nblk = sgn_channel_sum_blocks(P);
+  if (C % 8 != 0 || CV > 256 || (size_t)2 * (256 / CV) * C * sizeof(float) > 48 * 1024) return SG_FAST_UNSUPPORTED;
+  const int nblk = sgf_channel_sum_blocks(P);
   const int ppb = (int)((P + nblk - 1) / nblk);
   const size_t smem = (size_t)2 * (256 / CV) * C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;

@@ -164,6 +164,7 @@ class Generator(nn.Module):
                                          threshold=truncation_psi, beta=dlatent_avg_beta)
         else:
             self.truncation = None
+        self._avg_sync = None           # set by StyleGAN under data parallelism (models/_ddp.py)
 
     def forward(self, latents_in, depth, alpha, labels_in=None):
         if _host_facade.wants_facade(self, latents_in, labels_in):
@@ -185,6 +186,11 @@ class Generator(nn.Module):
         # training mode (reference GAN.py:274-293): W-average update from sample 0, style mixing, truncation.
         if self.truncation is not None:
             self.truncation.update(w1[0])
+            if self._avg_sync is not None:
+                # data parallel: every rank folded its own sample 0 into its copy (reference GAN.py:278 knows one
+                # process only); the replicas' buffers are averaged so that they stay identical (the EMA is linear,
+                # so this equals one EMA over the mean of the ranks' samples)
+                self._avg_sync(self.truncation.avg_latent)
         w2, cutoff = None, L
         if self.style_mixing_prob is not None and self.style_mixing_prob > 0:
             # host RNG consumption order identical to the reference: torch.randn on the CPU generator, then
@@ -331,6 +337,9 @@ class StyleGAN:
             self.gen_shadow = copy.deepcopy(self.gen)
             self.ema_updater = update_average
             self.ema_updater(self.gen_shadow, self.gen, beta=0)
+        if self.ddp is not None:
+            # after the shadow copy: gen_shadow is evaluated by rank 0 alone (sample grids) and must not join collectives
+            self.gen._avg_sync = self.ddp.average_
 
     def __setup_gen_optim(self, learning_rate, beta_1, beta_2, eps):
         self.gen_optim = FusedAdam(self.gen.parameters(), lr=learning_rate, betas=(float(beta_1), float(beta_2)),
@@ -390,7 +399,11 @@ class StyleGAN:
     def optimize_generator(self, noise, real_batch, depth, alpha, labels=None):
         """One generator update incl. gradient clipping and EMA (reference GAN.py:624-659)."""
         real_samples = None
-        if isinstance(self.loss, Losses.RelativisticAverageHingeGAN):
+        # the built-in losses below ignore the reals in gen_loss (reference Losses.py:84,128,151,227), so the pyramid
+        # the reference always computes (GAN.py:636) is skipped for them only; any other loss object receives it
+        ignores_reals = type(self.loss) in (Losses.LogisticGAN, Losses.HingeGAN, Losses.StandardGAN,
+                                            Losses.ConditionalGANLoss)
+        if not ignores_reals:
             with torch.no_grad():
                 real_samples = self.__progressive_down_sampling(real_batch, depth, alpha)
         fake_samples = self.gen(noise, depth, alpha, labels)
@@ -458,6 +471,16 @@ class StyleGAN:
             start_depth = self.depth - 1
         step = 1
         first_epoch, first_ticker = 1, 1
+        if self.ddp is not None and resume is None:
+            # torch's default CPU seed is the same constant in every process: without this all ranks would draw the
+            # same latents, style-mixing latents and NoiseLayer noise, i.e. `world` copies of one fake batch.
+            # fixed_input was drawn above, before the streams separate, so the sample grids do not depend on the rank.
+            from . import CustomLayers
+            base = torch.initial_seed() % (2 ** 31)
+            torch.manual_seed(base + self.ddp.rank)
+            random.seed(base + self.ddp.rank)
+            np.random.seed((base + self.ddp.rank) % (2 ** 32))
+            CustomLayers.manual_seed(base + self.ddp.rank)
         if resume is not None:
             state = _train_state.load(resume)
             start_depth, first_epoch, first_ticker, step = _train_state.resume_point(state, epochs)

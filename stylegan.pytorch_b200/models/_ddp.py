@@ -42,6 +42,15 @@ class DataParallelContext:
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t.data, src=src)
 
+    def average_(self, t):
+        """In-place mean of a small tensor over the ranks (Truncation.avg_latent after each update)."""
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:                                   # gloo (CPU host-logic tests) has no AVG
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.mul_(1.0 / self.world)
+        return t
+
     def reduce_buckets(self, grads):
         """grads: list of tensors (same device).  Returns (flats, placement) where flats are SUM-reduced flat
         buckets and placement[i] = (bucket_index, offset).  All-reduces are issued asynchronously; the caller must

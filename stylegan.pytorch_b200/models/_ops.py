@@ -7,6 +7,7 @@ backward pass without PyTorch having to see inside a kernel.  Generator-only Fun
 
 PyTorch is plumbing here: it owns memory, streams and the autograd tape; all arithmetic is in the kernels."""
 import ctypes
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -76,22 +77,27 @@ def _coef_dev(kind, k, direction, device):
 
 
 def cached_weight(W, sub, build):
-    """Derived (packed / scaled / bf16) copy of a weight, cached for nn.Parameters only, keyed on (storage, version,
-    weights epoch): the fused optimizer writes parameters through raw pointers and bumps the epoch instead of the
-    tensor version.  Code that edits `param.data` behind autograd's back must call clear_weight_cache()."""
+    """Derived (packed / scaled / bf16) copy of a weight, cached for nn.Parameters only.  An entry is valid for the
+    Parameter OBJECT it was built from (held by weak reference: ids and device pointers are recycled once a model is
+    freed, so neither may stand in for identity) at one (storage, version, weights epoch, shape): the fused
+    optimizer writes parameters through raw pointers and bumps the epoch instead of the tensor version.  Code that
+    edits `param.data` behind autograd's back must call clear_weight_cache()."""
     if not isinstance(W, torch.nn.Parameter):
         return build()
     key = (W.data_ptr(), W._version, _epoch[0], tuple(W.shape))
-    hit = _prep_cache.get(id(W))
-    if hit is not None and hit[0] == key:
+    wid = id(W)
+    hit = _prep_cache.get(wid)
+    if hit is not None and hit[2]() is W and hit[0] == key:
         E = hit[1].get(sub)
         if E is not None:
             return E
     else:
-        if len(_prep_cache) > 2048:
-            _prep_cache.clear()
-        hit = (key, {})
-        _prep_cache[id(W)] = hit
+        def _drop(ref, wid=wid):
+            cur = _prep_cache.get(wid)
+            if cur is not None and cur[2] is ref:
+                del _prep_cache[wid]
+        hit = (key, {}, weakref.ref(W, _drop))
+        _prep_cache[wid] = hit
     E = build()
     hit[1][sub] = E
     return E

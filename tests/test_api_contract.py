@@ -101,3 +101,32 @@ def test_bucketize():
     from models._ddp import bucketize
     assert bucketize([5, 5, 5, 20, 1], 10) == [[0, 1], [2], [3], [4]]
     assert bucketize([], 10) == []
+
+
+def test_weight_cache_is_keyed_on_the_parameter_object():
+    """ids and storage pointers are recycled after a model is freed: a fresh Parameter must never hit the derived
+    copy of a dead one (models/_ops.py cached_weight)."""
+    import gc
+    from models import _ops
+    _ops.clear_weight_cache()
+    seen = []
+    for i in range(1, 33):
+        W = torch.nn.Parameter(torch.full((8, 8), float(i)))
+        E = _ops.cached_weight(W, "k", lambda W=W: W.detach().clone())
+        again = _ops.cached_weight(W, "k", lambda: (_ for _ in ()).throw(AssertionError("must be a cache hit")))
+        assert again is E
+        seen.append(float(E[0, 0]))
+        del W, E, again
+        gc.collect()
+    assert seen == [float(i) for i in range(1, 33)]
+    assert len(_ops._prep_cache) == 0           # entries die with their parameters
+    # an edit through autograd-visible ops (version bump) or the fused optimizer (epoch bump) invalidates
+    W = torch.nn.Parameter(torch.zeros(4))
+    a = _ops.cached_weight(W, "k", lambda: W.detach().clone())
+    with torch.no_grad():
+        W.add_(1.0)
+    b = _ops.cached_weight(W, "k", lambda: W.detach().clone())
+    assert float(a[0]) == 0.0 and float(b[0]) == 1.0
+    W.data.fill_(5.0)
+    _ops.bump_weights_epoch()
+    assert float(_ops.cached_weight(W, "k", lambda: W.detach().clone())[0]) == 5.0

@@ -1,0 +1,123 @@
+"""The shape-specialised kernels behind sg_blur3 / sg_rgb_in / sg_rgb_out / sg_channel_sum (csrc/sg_blur_v2.cu,
+csrc/sg_rgb_k3.cu) against the general kernels of the same entry points (switch: sg_fast_paths) and against plain torch."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+class general_kernels:
+    def __enter__(self):
+        from models._lib import lib
+        self.old = lib.sg_fast_paths(0)
+
+    def __exit__(self, *a):
+        from models._lib import lib
+        lib.sg_fast_paths(self.old)
+
+
+def both(fn):
+    """fn() -> tensor; evaluated with the fast paths on and off."""
+    from models._lib import lib
+    assert lib.sg_fast_paths(-1) == 1
+    fast = fn()
+    with general_kernels():
+        slow = fn()
+    torch.cuda.synchronize()
+    return fast, slow
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(2, 8, 4, 8), (1, 16, 16, 64), (3, 8, 12, 16), (2, 64, 64, 128), (1, 8, 8, 512),
+                                   (2, 256, 256, 64)])
+def test_blur_fast_equals_general_and_torch(dt, shape):
+    from models._lib import lib, ptr, code
+    torch.manual_seed(1)
+    N, H, W, C = shape
+    x = torch.randn(N, H, W, C, device=DEV).to(dt)
+    bias = torch.randn(C, device=DEV)
+    k = torch.tensor([1.0, 2.0, 1.0], device=DEV)
+    k2 = (k[:, None] * k[None, :] / 16.0)[None, None].expand(C, 1, 3, 3)
+    for b in (None, bias):
+        def run():
+            out = torch.empty_like(x)
+            lib.sg_blur3(ptr(x), ptr(out), ptr(b), 0.5, code(dt), N, H, W, C, _s())
+            return out
+        fast, slow = both(run)
+        tol = 1e-6 if dt == torch.float32 else 4e-3
+        assert rel(fast.float(), slow.float()) < tol
+        ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), k2, padding=1, groups=C).permute(0, 2, 3, 1)
+        if b is not None:
+            ref = ref + 0.5 * b
+        assert rel(fast.float(), ref) < (1e-5 if dt == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("N,hw,C", [(2, 8, 16), (3, 5, 64), (1, 64, 128), (4, 16, 512), (2, 256, 64)])
+def test_rgb_in_fast_equals_general_and_torch(act, N, hw, C):
+    from models._lib import lib, ptr
+    torch.manual_seed(2)
+    img = torch.randn(N, 3, hw, hw, device=DEV)
+    W, b = torch.randn(C, 3, device=DEV), torch.randn(C, device=DEV)
+
+    def run():
+        out = torch.empty(N, hw, hw, C, device=DEV, dtype=torch.bfloat16)
+        lib.sg_rgb_in(ptr(img), ptr(W), ptr(b), 0.3, 1.0, act, ptr(out), 1, N, hw * hw, 3, C, _s())
+        return out
+    fast, slow = both(run)
+    assert rel(fast.float(), slow.float()) < 4e-3
+    ref = torch.einsum("nkhw,ck->nhwc", img, W) * 0.3 + b
+    if act:
+        ref = torch.nn.functional.leaky_relu(ref, 0.2)
+    assert rel(fast.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("up,beta", [(1, 0.0), (2, 0.0), (1, 0.7), (2, 0.4)])
+@pytest.mark.parametrize("N,hw,C", [(2, 16, 64), (1, 32, 128), (3, 16, 16), (1, 64, 256), (2, 128, 64)])
+def test_rgb_out_fast_equals_general_and_torch(up, beta, N, hw, C):
+    from models._lib import lib, ptr
+    torch.manual_seed(3)
+    x = torch.randn(N, hw, hw, C, device=DEV).to(torch.bfloat16)
+    W, b = torch.randn(3, C, device=DEV), torch.randn(3, device=DEV)
+    init = torch.randn(N, 3, hw * up, hw * up, device=DEV)
+
+    def run():
+        out = init.clone()
+        lib.sg_rgb_out(ptr(x), 1, ptr(W), ptr(b), 0.2, 1.0, 0.6, beta, ptr(out), N, hw, hw, C, 3, up, _s())
+        return out
+    fast, slow = both(run)
+    assert rel(fast, slow) < 1e-5
+    rgb = (torch.einsum("nhwc,kc->nkhw", x.float(), W) * 0.2 + b.view(1, 3, 1, 1)) * 0.6
+    if up == 2:
+        rgb = rgb.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    assert rel(fast, beta * init + rgb) < 1e-5
+
+
+@pytest.mark.parametrize("N,hw,C", [(2, 8, 16), (3, 31, 64), (1, 64, 128), (2, 16, 512), (2, 256, 64)])
+def test_channel_sum_fast_equals_general_and_torch(N, hw, C):
+    from models._lib import lib, ptr
+    torch.manual_seed(4)
+    P = N * hw * hw
+    x = torch.randn(N, hw, hw, C, device=DEV).to(torch.bfloat16)
+    wt = torch.randn(N, 1, hw, hw, device=DEV)
+
+    def run():
+        out = torch.empty(2, C, device=DEV)
+        ws = torch.empty(lib.sg_channel_sum_blocks(P) * 2 * C, device=DEV)
+        lib.sg_channel_sum(ptr(x), 1, ptr(wt), 1, 1, P, hw * hw, C, ptr(ws), ptr(out), 0.5, 0, _s())
+        return out
+    fast, slow = both(run)
+    assert rel(fast, slow) < 1e-4
+    xf = x.float().reshape(P, C)
+    ref = torch.stack([(wt.reshape(P, 1) * xf).sum(0), xf.sum(0)]) * 0.5
+    assert rel(fast, ref) < 1e-4

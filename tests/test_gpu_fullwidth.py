@@ -1,0 +1,134 @@
+"""BASELINE configs 2 and 3 at the reference's REAL channel widths (128x128 depth 5 and 256x256 depth 6, batch 4) against
+golden outputs of the live reference (oracle/make_golden.py --full -> tests/golden/full*.pt).  The inputs are re-derived
+on the GPU box from the fixture's seed (oracle.seeded_case); the fixture holds only what the reference produced.
+
+fp32 engine: the north-star tolerance, 1e-3 relative per tensor (gradient tensors: 3e-3 on the norm, 5e-3 on the head,
+LeakyReLU mask flips amplify a forward error eps into ~sqrt(eps) of gradient error).
+bf16 engine (the benchmarked tcgen05 path): a stated bound for EVERY compared tensor, see BF16_TOL below.  The observed
+errors are written to gpurun_out/fullwidth_errors_<name>_<precision>.json so that the bounds can be audited."""
+import json
+import os
+import random
+
+import pytest
+import torch
+
+import stylegan_oracle as O
+from test_oracle_golden import arch_from
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FP32_TOL = dict(image=1e-3, avg=1e-4, logits=1e-3, r1=2e-3, loss=1e-3, grad_norm=3e-3, grad_head=5e-3, grad_full=3e-3)
+# bf16 activations + bf16 tensor-core operands, fp32 accumulation; 8 mantissa bits = 3.9e-3 per rounding, ~30 layers deep.
+# image/logits: relative L2 of the tensor; r1/loss: relative; grad_norm: relative error of the per-parameter gradient
+# norm; grad_head / grad_full: relative L2 of the first 64 / all elements of the gradient.
+BF16_TOL = dict(image=3e-2, avg=1e-4, logits=6e-2, r1=1.5e-1, loss=2e-2, grad_norm=1e-1, grad_head=2.5e-1,
+                grad_full=2.5e-1)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+class FixedMixing:
+    def __init__(self, z2, cutoff):
+        self.z2, self.cutoff = z2, cutoff
+
+    def __enter__(self):
+        self._randn, self._random, self._randint = torch.randn, random.random, random.randint
+        me = self
+
+        def fake_randn(*a, **k):
+            torch.randn = me._randn
+            return me.z2.clone()
+        torch.randn = fake_randn
+        random.random = lambda: 0.0
+        random.randint = lambda a, b: self.cutoff
+
+    def __exit__(self, *a):
+        torch.randn, random.random, random.randint = self._randn, self._random, self._randint
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["full128_d5", "full256_d6"])
+def test_full_width_vs_reference_golden(golden_dir, name, precision):
+    import models
+    from models import Losses, _ops
+    from models.GAN import Generator, Discriminator
+    from models.CustomLayers import NoiseLayer
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    arch = arch_from(fx["arch"])
+    depth, alpha, batch = fx["depth"], fx["alpha"], fx["batch"]
+    case = O.seeded_case(arch, batch, depth, fx["seed"])
+    tol = FP32_TOL if precision == "fp32" else BF16_TOL
+    seen = {}
+
+    def check(kind, key, err):
+        seen.setdefault(kind, {})[key] = err
+        assert err <= tol[kind], "%s %s: %.3e > %.1e (%s)" % (kind, key, err, tol[kind], precision)
+
+    models.set_precision(precision)
+    _ops.clear_weight_cache()
+    try:
+        g = Generator(**arch.g_kwargs()).to(DEV)
+        d = Discriminator(**arch.d_kwargs()).to(DEV)
+        g.load_state_dict(case["g_sd"]); d.load_state_dict(case["d_sd"])
+        _ops.clear_weight_cache()
+        g.train(); d.train()
+        for m, n in zip([m for m in g.g_synthesis.modules() if isinstance(m, NoiseLayer)], case["noises"]):
+            m.noise = n.to(DEV)
+        z, real = case["z"].to(DEV), case["real"].to(DEV)
+        with torch.no_grad():
+            for d_, ref in fx["lower"].items():
+                avg0 = g.truncation.avg_latent.clone()
+                with FixedMixing(case["z2"], min(case["cutoff"], 2 * (d_ + 1))):
+                    check("image", "depth%d_alpha1" % d_, rel(g(z, d_, 1.0), ref))
+                g.truncation.avg_latent.copy_(avg0)
+        with FixedMixing(case["z2"], case["cutoff"]):
+            fake = g(z, depth, alpha)
+        check("image", "fake_depth%d" % depth, rel(fake, fx["fake"]))
+        check("avg", "truncation.avg_latent", rel(g.truncation.avg_latent, fx["avg_after"]))
+        # the discriminator is checked on the REFERENCE's fake image so that generator error does not leak into it
+        fake_ref = fx["fake"].to(DEV)
+        check("logits", "D(fake_ref)", rel(d(fake_ref, depth, alpha), fx["logits_fake"]))
+        check("logits", "D(real)", rel(d(real, depth, alpha), fx["logits_real"]))
+        loss = Losses.LogisticGAN(d)
+        r1 = loss.R1Penalty(real, depth, alpha)
+        check("r1", "R1", abs(float(r1) - fx["r1"]) / abs(fx["r1"]))
+        d_loss = loss.dis_loss(real, fake_ref, depth, alpha)
+        check("loss", "d_loss", abs(float(d_loss) - fx["d_loss"]) / abs(fx["d_loss"]))
+        names = [n for n, _ in d.named_parameters()]
+        grads = torch.autograd.grad(d_loss, list(d.parameters()), allow_unused=True)
+        for n, gr in zip(names, grads):
+            if gr is None:
+                assert n not in fx["d_grads"], n
+                continue
+            ref = fx["d_grads"][n]
+            check("grad_norm", "D." + n, abs(float(gr.norm()) - ref["norm"]) / (ref["norm"] + 1e-12))
+            check("grad_head", "D." + n, rel(gr.flatten()[:64], ref["head"]))
+            if ref["full"] is not None:
+                check("grad_full", "D." + n, rel(gr, ref["full"]))
+        del grads, d_loss, r1
+        g_loss = loss.gen_loss(None, fake, depth, alpha)
+        check("loss", "g_loss", abs(float(g_loss) - fx["g_loss"]) / abs(fx["g_loss"]))
+        names = [n for n, _ in g.named_parameters()]
+        grads = torch.autograd.grad(g_loss, list(g.parameters()), allow_unused=True)
+        for n, gr in zip(names, grads):
+            if gr is None:
+                assert n not in fx["g_grads"], n
+                continue
+            ref = fx["g_grads"][n]
+            check("grad_norm", "G." + n, abs(float(gr.norm()) - ref["norm"]) / (ref["norm"] + 1e-12))
+            check("grad_head", "G." + n, rel(gr.flatten()[:64], ref["head"]))
+            if ref["full"] is not None:
+                check("grad_full", "G." + n, rel(gr, ref["full"]))
+    finally:
+        models.set_precision("fp32")
+        out = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out):
+            worst = {k: max(v.items(), key=lambda kv: kv[1]) for k, v in seen.items() if v}
+            json.dump({"worst": worst, "tolerance": tol, "all": seen},
+                      open(os.path.join(out, "fullwidth_errors_%s_%s.json" % (name, precision)), "w"), indent=1)

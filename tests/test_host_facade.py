@@ -48,7 +48,7 @@ def test_no_facade_without_cuda():
     assert not hf.wants_facade(_M(), torch.zeros(2, 3))
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_generate_script_calling_convention_on_gpu():
     """CPU Generator + CPU latents, as generate_samples.py / generate_mixing_figure.py use it."""
     import numpy as np

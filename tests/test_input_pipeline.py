@@ -31,7 +31,7 @@ def test_reference_transform_matches_torchvision_formula():
     assert float(got.min()) >= -1.0 and float(got.max()) <= 1.0
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(4, 16, 16, 3), (3, 7, 5, 3), (2, 9, 4, 1), (1, 256, 256, 3)])
 def test_prep_images_bit_exact_on_gpu(shape):
     torch.manual_seed(3)

@@ -127,3 +127,31 @@ def test_state_dict_key_contract():
         a = O.Arch(res, fmap_base=64, fmap_max=8, latent_size=8, dlatent_size=8, mapping_layers=4)
         assert len(O.init_generator(a)) == ng
         assert len(O.init_discriminator(a)) == nd
+
+
+@pytest.mark.parametrize("name,deep", [("full128_d5", True), ("full256_d6", False)])
+def test_full_width_fixture_matches_oracle(golden_dir, name, deep):
+    """BASELINE configs 2/3 at real channel widths: the seed-derived inputs (O.seeded_case) reproduce, through the oracle,
+    what the live reference produced (forward at every depth; for 128x128 also logits, R1 and the discriminator loss)."""
+    fx = load(golden_dir, name)
+    arch = arch_from(fx["arch"])
+    depth, alpha = fx["depth"], fx["alpha"]
+    case = O.seeded_case(arch, fx["batch"], depth, fx["seed"])
+    g = {k: v.clone() for k, v in case["g_sd"].items()}
+    with torch.no_grad():
+        for d_, ref in fx["lower"].items():
+            avg0 = g["truncation.avg_latent"].clone()
+            img = O.generator_forward(g, case["z"], d_, 1.0, arch, z2=case["z2"],
+                                      mixing_cutoff=min(case["cutoff"], 2 * (d_ + 1)), noises=case["noises"])
+            assert rel(img, ref) < TOL, d_
+            g["truncation.avg_latent"].copy_(avg0)
+        fake = O.generator_forward(g, case["z"], depth, alpha, arch, z2=case["z2"], mixing_cutoff=case["cutoff"],
+                                   noises=case["noises"])
+    assert rel(fake, fx["fake"]) < TOL
+    assert rel(g["truncation.avg_latent"], fx["avg_after"]) < TOL
+    if deep:
+        d = case["d_sd"]
+        with torch.no_grad():
+            assert rel(O.discriminator(d, fx["fake"], depth, alpha, arch), fx["logits_fake"]) < TOL
+        r1 = O.r1_penalty(d, case["real"], depth, alpha, arch)
+        assert abs(float(r1) - fx["r1"]) <= 1e-3 * abs(fx["r1"])

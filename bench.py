@@ -383,6 +383,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="bf16")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -390,6 +391,14 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.impl == "gpu_baseline":
+        t0 = time.time()
+        msb = gpu_oracle_step_time(args.res, args.batch, 3, 1, args.mode)
+        print(json.dumps({"value": round(args.batch / (msb * 1e-3), 2), "ms_per_step": round(msb, 2),
+                          "wall_s_incl_warmup": round(time.time() - t0, 1),
+                          "how": "autocast(bfloat16) + channels_last, cudnn.benchmark=True" if args.mode == "bf16"
+                                 else "fp32, cudnn.benchmark=True (reference train.py:77)"}))
+        return
 
     import torch
     import torch.distributed as dist
@@ -511,11 +520,15 @@ def main():
             del sg
             gc.collect(); torch.cuda.empty_cache()
             for mode in ("bf16", "fp32"):
+                # own process + time limit: cudnn.benchmark autotunes every new conv shape (fwd, dgrad, wgrad and their
+                # double-backward forms) during the warm-up step, which can take minutes
                 try:
-                    msb = gpu_oracle_step_time(R, B, 3, 1, mode)
-                    gb[mode] = {"value": round(B / (msb * 1e-3), 2), "ms_per_step": round(msb, 2),
-                                "how": "autocast(bfloat16) + channels_last" if mode == "bf16"
-                                       else "fp32, cudnn.benchmark=True (reference train.py:77)"}
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "gpu_baseline", "--mode",
+                                        mode, "--res", str(R), "--batch", str(B)], capture_output=True, text=True,
+                                       timeout=float(os.environ.get("SG_GPU_BASELINE_TIMEOUT", "150")))
+                    gb[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+                except subprocess.TimeoutExpired:
+                    gb[mode] = {"error": "timeout"}
                 except Exception as e:
                     gb[mode] = {"error": str(e)[:160]}
             best = max((gb[m].get("value", 0.0) for m in ("bf16", "fp32")), default=0.0)

@@ -69,6 +69,29 @@ int sg_conv3x3_tc_supported(int N, int H, int W, int Cin, int Cout);
 int sg_conv3x3_tc(const void* x, const void* Etc, void* y, const float* bias, float bias_mul, int act, int N, int H,
                   int W, int Cin, int Cout, void* stream);
 
+/* CTA-pair (tcgen05 cta_group::2, M = 256) form of the same convolution with the first half of LayerEpilogue fused into
+ * the epilogue (csrc/sg_conv_pair_tc.cu): z = [lrelu](conv + bias*bias_mul + noise_w[c]*noise[n,h,w]) written once in
+ * bf16, plus -- when `part` is given -- per-(image, CTA slot) partial sums of z and z^2 per channel for
+ * nn.InstanceNorm2d (models/CustomLayers.py:191-200, :233 after :170-171).  noise fp32 [N,H,W] or null; part fp32
+ * [N][sg_conv3x3_pair_slots][2][Cout] or null.  sg_epi_finalize_parts reduces the slots in fixed order (fp64) and
+ * writes mr [N,Cout,2] = (mean, rstd) and ab [N,Cout,3] = (mean, rstd*(1+s0), s1) like sg_epi_finalize. */
+int sg_conv3x3_pair_supported(int N, int H, int W, int Cin, int Cout);
+int sg_conv3x3_pair_slots(int N, int H, int W, int Cin, int Cout);
+int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const float* bias, float bias_mul, int act,
+                    const float* noise, const float* noise_w, float* part, int N, int H, int W, int Cin, int Cout,
+                    void* stream);
+int sg_epi_finalize_parts(const float* part, const float* style, float* mr, float* ab, int N, int H, int W, int Cin,
+                          int Cout, float eps, void* stream);
+
+/* BlurLayer + bias + the front half of LayerEpilogue in one pass (csrc/sg_blur_v2.cu; models/CustomLayers.py:174-180
+ * then :242-246): z = lrelu(blur3(x) + bias*bias_mul + noise_w[c]*noise[n,h,w]) in bf16 and per-(image, block) partial
+ * sums of z, z^2 (part [N][sg_blur3_epi_slots][2][C]); sg_epi_finalize_slots reduces them like sg_epi_finalize_parts. */
+int sg_blur3_epi_slots(int N, int H, int W, int C);
+int sg_blur3_epi(const void* x, void* z, const float* bias, float bias_mul, const float* noise, const float* noise_w,
+                 float* part, int N, int H, int W, int C, void* stream);
+int sg_epi_finalize_slots(const float* part, int slots, const float* style, float* mr, float* ab, int N, int C, int HW,
+                          float eps, void* stream);
+
 /* tcgen05/TMA up-/down-sampling convolutions in the tap-merged low-resolution form (csrc/sg_convud_tc.cu):
  * mode 0 UP   x [N,H,W,Cin] -> y [N,2H,2W,Cout], 4 phases x 2x2 taps  (CustomLayers.py:143-154 upscale conv; dgrad of down)
  * mode 1 DOWN x [N,2H,2W,Cin] -> y [N,H,W,Cout], 4x4 taps stride 2    (CustomLayers.py:156-180 downscale conv; dgrad of up)

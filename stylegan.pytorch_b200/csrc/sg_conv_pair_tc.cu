@@ -1,0 +1,568 @@
+// CTA-pair (tcgen05 cta_group::2) implicit-GEMM 3x3 stride-1 convolution for sm_100a with the synthesis-layer epilogue
+// fused in:
+//
+//   z[n,h,w,co] = act( sum_{kh,kw,ci} x[n,h+kh-1,w+kw-1,ci] * E[kh*3+kw][co][ci] + bias[co]*bias_mul
+//                      + noise_w[co] * noise[n,h,w] )                                     (bf16, written once)
+//   part[n][slot][0][co] = sum over the CTA's pixels of image n of z,   part[n][slot][1][co] = same of z^2
+//
+// reference call sites: EqualizedConv2d.forward -> F.conv2d (models/CustomLayers.py:170-171) followed by the first
+// half of LayerEpilogue.forward (NoiseLayer :191-200, LeakyReLU, and the statistics nn.InstanceNorm2d :233 needs);
+// with noise/part null it is the plain fused-bias/LeakyReLU convolution and its dgrad (discriminator, backward).
+//
+// Why a CTA pair: a 128xNx16 cta_group::1 MMA never issues faster than one per ~61-68 cycles on this part whatever N is
+// (profiles/r01_mma_rate.txt), which caps the 64-output-channel layers at 0.58 of the measured bf16 peak; the
+// cta_group::2 form (M = 256: 128 pixels from each CTA, each CTA holding N/2 rows of the weights) measured 43 cycles at
+// N = 64 and 64 at N = 128 (profiles/r02_mma_rate2.txt: 1573 / 2046 TFLOP/s chip-wide with operands resident).
+//
+// Structure per CTA (both CTAs of the cluster): warp 0 TMA producer (own activation halo box + own half of the weights,
+// completion signalled on the LEADER's mbarrier via the cta_group::2 TMA form), warp 1 MMA issuer (leader CTA only),
+// warps 2-5 epilogue of the CTA's own 128-pixel tile.  A pair walks a CONTIGUOUS range of tile pairs, so the per-image
+// statistics are accumulated in registers across tiles and flushed once per (CTA, image): deterministic two-stage
+// reduction, no atomics (sg_epi_finalize_parts sums the slots in fixed order).
+#include "sg_common.cuh"
+#include "../../include/sgb200.h"
+#include "sg_tc_common.cuh"
+
+namespace tc2 {
+
+using namespace tcu;
+
+constexpr int TH = 8, TW = 16, BK = 64;
+constexpr int HALO_ROWS = (TH + 2) * TW;           // 160 smem rows of 128 B per kw-shift
+constexpr int A_BYTES = HALO_ROWS * BK * 2;        // 20480
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+struct __align__(8) Barriers {
+  uint64_t full[MAX_STAGES];      // leader's copy is used: expect_tx by the leader, complete_tx from both CTAs' TMA
+  uint64_t empty[MAX_STAGES];     // each CTA's own copy, arrived by the leader's multicast tcgen05.commit
+  uint64_t tmem_full[2];          // each CTA's own copy (multicast commit)
+  uint64_t tmem_empty[2];         // leader's copy: 4 epilogue warps of each CTA arrive (count 8)
+  uint64_t wfull;                 // leader's copy: resident weights of both CTAs have landed
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct Params {
+  int N, H, W, Cin, Cout, BN, HB;                 // BN = MMA N (both halves), HB = BN/2 = weight rows per CTA
+  int tiles_h, tiles_w, tiles_n, num_spatial, tiles_per_image;
+  int Q, pairs;                                   // tile pairs per N block, clusters per N block
+  int kchunks, stages, stage_bytes, tmem_cols;
+  int resident, w_bytes;
+  const float* bias;
+  float bias_mul;
+  int act;
+  const float* noise;                             // [N,H,W] fp32 or null
+  const float* noise_w;                           // [Cout]
+  float* part;                                    // [N][slots][2][Cout] fp32 or null; slots = 2*pairs
+  __nv_bfloat16* y;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+// TMA loads of a CTA pair: the bytes land in the executing CTA's shared memory, the completion goes to the mbarrier at
+// the same offset in the LEADER CTA (rank bit cleared), which the MMA-issuing warp waits on.
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 da, db;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n"
+      " setp.ne.b32 p, %6, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)0x3)
+               : "memory");
+}
+
+// 64 per-lane values (one per channel of this lane's pixel) -> per-warp column sums, two channels per lane:
+// lane l ends up with the sums of channels 2l and 2l+1 in out0/out1.  31 exchange rounds halve the live set each time.
+__device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane, float& out0, float& out1) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {             // keep channels whose bit 5 == lane bit 4
+    const bool up = lane & 16;
+    const float keep = up ? v[i + 32] : v[i], send = up ? v[i] : v[i + 32];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 8;
+    const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 4;
+    const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 2;
+    const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 1;
+    const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  out0 = v[0];
+  out1 = v[1];
+}
+// channel held by (lane, j) after warp_colsum64: bit5 = lane bit4, bit4 = lane bit3, ..., bit1 = lane bit0, bit0 = j
+__device__ __forceinline__ int colsum_channel(int lane, int j) {
+  return ((lane & 16) << 1) | ((lane & 8) << 1) | ((lane & 4) << 1) | ((lane & 2) << 1) | ((lane & 1) << 1) | j;
+}
+
+template <bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem + (size_t)p.stages * p.stage_bytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_w + p.w_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader_cta = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int nt = cluster_id % p.tiles_n;                 // this pair's N block
+  const int j = cluster_id / p.tiles_n;                  // pair index inside the N block
+  const int n0 = nt * p.BN;
+  // contiguous range of tile pairs
+  const int q_begin = (int)((long long)j * p.Q / p.pairs), q_end = (int)((long long)(j + 1) * p.Q / p.pairs);
+
+  __shared__ float s_bias[256], s_nw[256];
+  __shared__ float s_red[4][2][64];                      // cross-warp combine of the statistics (one 64-ch chunk)
+  for (int i = threadIdx.x; i < p.BN; i += blockDim.x) {
+    s_bias[i] = p.bias ? p.bias[n0 + i] * p.bias_mul : 0.f;
+    s_nw[i] = (p.noise && p.noise_w) ? p.noise_w[n0 + i] : 0.f;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 8); }
+    mbar_init(&bars->wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_w);
+  }
+  if (warp == 1) {                                        // one warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // both CTAs' barriers initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int b_tap_bytes = p.HB * BK * 2;                  // one tap of this CTA's half of the weights
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const int wrow0 = n0 + (int)rank * p.HB;
+      if (p.resident) {
+        if (leader_cta) mbar_expect_tx(&bars->wfull, (uint32_t)(2 * p.w_bytes));
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int t = 0; t < 9; ++t)
+            tma2_load_2d(smem_w + (size_t)(kc * 9 + t) * b_tap_bytes, &map_w, &bars->wfull, kc * BK, t * p.Cout + wrow0);
+      }
+      const uint32_t stage_tx = (uint32_t)(2 * (p.resident ? A_BYTES : A_BYTES + 3 * b_tap_bytes));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int q = q_begin; q < q_end; ++q) {
+        int r = 2 * q + (int)rank;
+        int wt = r % p.tiles_w; r /= p.tiles_w;
+        int ht = r % p.tiles_h;
+        int n = r / p.tiles_h;
+        const int h0 = ht * TH, w0 = wt * TW;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int kw = 0; kw < 3; ++kw) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
+            uint8_t* sB = sA + A_BYTES;
+            if (leader_cta) mbar_expect_tx(&bars->full[stage], stage_tx);
+            tma2_load_4d(sA, &map_x, &bars->full[stage], kc * BK, w0 + kw - 1, h0 - 1, n);
+            if (!p.resident)
+              for (int kh = 0; kh < 3; ++kh)
+                tma2_load_2d(sB + kh * b_tap_bytes, &map_w, &bars->full[stage], kc * BK,
+                             (kh * 3 + kw) * p.Cout + wrow0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader_cta) {
+      const uint32_t idesc = make_idesc_bf16(256, p.BN);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t sW = smem_u32(smem_w);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (p.resident) { mbar_wait(&bars->wfull, 0); tc_fence_after(); }
+      const uint32_t b_kh_stride = p.resident ? (uint32_t)(3 * b_tap_bytes) : (uint32_t)b_tap_bytes;
+      for (int q = q_begin; q < q_end; ++q) {
+        mbar_wait_cluster(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+        for (int it = 0; it < p.kchunks * 3; ++it) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_base + (uint32_t)(stage * p.stage_bytes);
+          const int kw = it % 3, kc = it / 3;
+          const uint32_t sB = p.resident ? (sW + (uint32_t)((kc * 9 + kw) * b_tap_bytes)) : (sA + A_BYTES);
+          const uint64_t a0 = make_desc_sw128(sA);
+          const uint64_t b0 = make_desc_sw128(sB);
+          const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
+          const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
+          const uint32_t bstep = b_kh_stride >> 4;
+          const bool leader = elect_one_sync();
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t al = a_lo + (uint32_t)((kh * (TW * 128) + k * 32) >> 4);
+              const uint32_t bl = b_lo + kh * bstep + (uint32_t)((k * 32) >> 4);
+              if (leader) umma2_bf16_lohi(tmem_d, al, a_hi, bl, b_hi, idesc, (it | kh | k) ? 1u : 0u);
+            }
+          }
+          if (leader) umma2_commit(&bars->empty[stage]);
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one_sync()) umma2_commit(&bars->tmem_full[acc]);
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quadrant = warp % 4), both CTAs =====================
+    const int qd = warp & 3;
+    const int m = qd * 32 + lane;
+    const int pr = m / TW, pc = m % TW;
+    const uint32_t empty_remote = mapa_u32(smem_u32(&bars->tmem_empty[0]), 0);
+    const int slot = 2 * j + (int)rank;
+    const int slots = 2 * p.pairs;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    // running per-warp statistics of the current image: lane holds channels colsum_channel(lane, 0/1) of each chunk
+    float st_s[4][2], st_q[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { st_s[c][0] = st_s[c][1] = st_q[c][0] = st_q[c][1] = 0.f; }
+    int cur_n = -1;
+    const int nchunks = p.BN / 64;
+
+    auto flush = [&](int n) {
+      // combine the four epilogue warps through shared memory in a fixed order and write this CTA's slot of image n
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= nchunks) break;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        s_red[qd][0][colsum_channel(lane, 0)] = st_s[c][0];
+        s_red[qd][0][colsum_channel(lane, 1)] = st_s[c][1];
+        s_red[qd][1][colsum_channel(lane, 0)] = st_q[c][0];
+        s_red[qd][1][colsum_channel(lane, 1)] = st_q[c][1];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t = qd * 32 + lane;                      // 128 threads: 2 quantities x 64 channels
+        const int which = t >> 6, ch = t & 63;
+        const float s = (s_red[0][which][ch] + s_red[1][which][ch]) + (s_red[2][which][ch] + s_red[3][which][ch]);
+        p.part[(((size_t)n * slots + slot) * 2 + which) * p.Cout + n0 + c * 64 + ch] = s;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { st_s[c][0] = st_s[c][1] = st_q[c][0] = st_q[c][1] = 0.f; }
+    };
+
+    for (int q = q_begin; q < q_end; ++q) {
+      int r = 2 * q + (int)rank;
+      int wt = r % p.tiles_w; r /= p.tiles_w;
+      int ht = r % p.tiles_h;
+      int n = r / p.tiles_h;
+      if (STATS) {
+        if (n != cur_n && cur_n >= 0) flush(cur_n);
+        cur_n = n;
+      }
+      const int hh = ht * TH + pr, ww = wt * TW + pc;
+      const size_t pix = ((size_t)n * p.H + hh) * p.W + ww;
+      const float nz = p.noise ? p.noise[pix] : 0.f;        // issued before the wait: latency hidden behind the MMAs
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      __nv_bfloat16* dst = p.y + pix * p.Cout + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.BN);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= nchunks) break;
+        const int c0 = c * 64;
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        tmem_ld16_nowait(taddr + c0, v0);
+        tmem_ld16_nowait(taddr + c0 + 16, v1);
+        tmem_ld16_nowait(taddr + c0 + 32, v2);
+        tmem_ld16_nowait(taddr + c0 + 48, v3);
+        tmem_ld_wait();
+        float zf[64];
+        auto emit16 = [&](const uint32_t (&v)[16], int o) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            float a = __uint_as_float(v[2 * jj]) + s_bias[c0 + o + 2 * jj];
+            float b = __uint_as_float(v[2 * jj + 1]) + s_bias[c0 + o + 2 * jj + 1];
+            if (p.noise) {
+              a = fmaf(s_nw[c0 + o + 2 * jj], nz, a);
+              b = fmaf(s_nw[c0 + o + 2 * jj + 1], nz, b);
+            }
+            if (p.act) { a = fmaxf(a, SG_LRELU_SLOPE * a); b = fmaxf(b, SG_LRELU_SLOPE * b); }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+            const uint32_t w = *reinterpret_cast<uint32_t*>(&h2);
+            packed[jj] = w;
+            if (STATS) {                                    // statistics of the ROUNDED values (what the consumer reads)
+              zf[o + 2 * jj] = __uint_as_float(w << 16);
+              zf[o + 2 * jj + 1] = __uint_as_float(w & 0xffff0000u);
+            }
+          }
+          st_global_256(dst + c0 + o, packed);
+        };
+        emit16(v0, 0);
+        emit16(v1, 16);
+        emit16(v2, 32);
+        emit16(v3, 48);
+        if (STATS) {
+          float sq[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) sq[i] = zf[i] * zf[i];
+          float a0, a1, b0, b1;
+          warp_colsum64(zf, lane, a0, a1);
+          warp_colsum64(sq, lane, b0, b1);
+          st_s[c][0] += a0; st_s[c][1] += a1;
+          st_q[c][0] += b0; st_q[c][1] += b1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader_cta) mbar_arrive(&bars->tmem_empty[acc]);
+        else mbar_arrive_remote(empty_remote + (uint32_t)(acc * 8));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (STATS && cur_n >= 0) flush(cur_n);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // the leader's MMAs read the peer's shared memory until here
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// Second stage of the statistics: per (n, c) sum the slots of the CTAs that visited image n, in slot order, in fp64;
+// then mean / rstd and the folded InstanceNorm + StyleMod affine (same outputs as sg_epi_finalize).
+// A CTA (cluster jj, rank r) visits tiles 2q + r, q in [jj*Q/pairs, (jj+1)*Q/pairs); image n owns tiles [n*T, (n+1)*T).
+__global__ void finalize_parts_kernel(const float* __restrict__ part, const float* __restrict__ style,
+                                      float* __restrict__ mr, float* __restrict__ ab, int N, int C, int HW, int T, int Q,
+                                      int pairs, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  const int slots = 2 * pairs;
+  double s1 = 0.0, s2 = 0.0;
+  for (int s = 0; s < slots; ++s) {
+    const int jj = s >> 1, r = s & 1;
+    const int qb = (int)((long long)jj * Q / pairs), qe = (int)((long long)(jj + 1) * Q / pairs);
+    if (qe <= qb) continue;
+    int lo = max(n * T, 2 * qb + r);
+    if ((lo - r) & 1) ++lo;
+    const int hi = min((n + 1) * T - 1, 2 * (qe - 1) + r);
+    if (lo > hi) continue;
+    const float* q = part + (((size_t)n * slots + s) * 2) * C + c;
+    s1 += (double)q[0];
+    s2 += (double)q[C];
+  }
+  const double m = s1 / HW;
+  double var = s2 / HW - m * m;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float mean = (float)m;
+  mr[(size_t)i * 2] = mean;
+  mr[(size_t)i * 2 + 1] = rstd;
+  const float st0 = style ? style[(size_t)n * 2 * C + c] : 0.f;
+  const float st1 = style ? style[(size_t)n * 2 * C + C + c] : 0.f;
+  ab[(size_t)i * 3] = mean;
+  ab[(size_t)i * 3 + 1] = rstd * (1.f + st0);
+  ab[(size_t)i * 3 + 2] = st1;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static int pick_bn(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout == 128 || Cout == 64) return Cout;
+  return 0;
+}
+static bool resident_ok(int Cin, int HB) { return 9 * (Cin / BK) * HB * BK * 2 <= 150 * 1024; }
+
+struct Plan {
+  int BN, HB, tiles_n, num_spatial, Q, pairs, kchunks, resident, w_bytes, stage_bytes, stages, tmem_cols, grid;
+  size_t smem;
+};
+
+static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl) {
+  if (N < 1 || H % TH != 0 || W % TW != 0 || Cin % BK != 0 || Cin < BK) return false;
+  const int BN = pick_bn(Cout);
+  if (!BN) return false;
+  pl->BN = BN; pl->HB = BN / 2;
+  pl->tiles_n = Cout / BN;
+  pl->num_spatial = N * (H / TH) * (W / TW);
+  if (pl->num_spatial % 2 != 0) return false;
+  pl->Q = pl->num_spatial / 2;
+  pl->kchunks = Cin / BK;
+  pl->resident = resident_ok(Cin, pl->HB) ? 1 : 0;
+  pl->w_bytes = pl->resident ? 9 * pl->kchunks * pl->HB * BK * 2 : 0;
+  pl->stage_bytes = pl->resident ? A_BYTES : A_BYTES + 3 * pl->HB * BK * 2;
+  int stages = (214 * 1024 - pl->w_bytes) / pl->stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return false;
+  pl->stages = stages;
+  int cols = 32;
+  while (cols < 2 * BN) cols <<= 1;
+  pl->tmem_cols = cols;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = (sms / 2) / pl->tiles_n;                     // clusters per N block
+  if (pairs > pl->Q) pairs = pl->Q;
+  if (pairs < 1) return false;
+  pl->pairs = pairs;
+  pl->grid = pairs * pl->tiles_n * 2;
+  pl->smem = (size_t)stages * pl->stage_bytes + pl->w_bytes + sizeof(Barriers) + 1024;
+  return true;
+}
+
+template <bool STATS>
+static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, const Plan& pl, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(conv3x3_pair_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+  });
+  if (err != cudaSuccess) { sg_set_error("sg_conv3x3_pair: cannot raise the dynamic shared memory limit"); return (int)err; }
+  conv3x3_pair_kernel<STATS><<<pl.grid, NUM_THREADS, pl.smem, st>>>(mx, mw, p);
+  return sg_check_launch("sg_conv3x3_pair");
+}
+
+}  // namespace tc2
+
+SG_EXPORT int sg_conv3x3_pair_supported(int N, int H, int W, int Cin, int Cout) {
+  tc2::Plan pl;
+  return tc2::make_plan(N, H, W, Cin, Cout, &pl) ? 1 : 0;
+}
+
+// number of statistic slots per image written by sg_conv3x3_pair (0 if unsupported)
+SG_EXPORT int sg_conv3x3_pair_slots(int N, int H, int W, int Cin, int Cout) {
+  tc2::Plan pl;
+  return tc2::make_plan(N, H, W, Cin, Cout, &pl) ? 2 * pl.pairs : 0;
+}
+
+SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const float* bias, float bias_mul, int act,
+                              const float* noise, const float* noise_w, float* part, int N, int H, int W, int Cin,
+                              int Cout, void* stream) {
+  using namespace tc2;
+  Plan pl;
+  SG_REQUIRE(make_plan(N, H, W, Cin, Cout, &pl), "sg_conv3x3_pair: shape not supported");
+  EncodeTiledFn enc = get_encode();
+  SG_REQUIRE(enc != nullptr, "sg_conv3x3_pair: cuTensorMapEncodeTiled unavailable");
+  CUtensorMap map_x, map_w;
+  SG_REQUIRE(encode_nhwc(&map_x, x, N, H, W, Cin, TW, TH + 2), "sg_conv3x3_pair: cuTensorMapEncodeTiled(x) failed");
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)9 * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)pl.HB};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(Etc), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SG_REQUIRE(r == CUDA_SUCCESS, "sg_conv3x3_pair: cuTensorMapEncodeTiled(w) failed");
+  }
+  Params p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.BN = pl.BN; p.HB = pl.HB;
+  p.tiles_h = H / TH; p.tiles_w = W / TW; p.tiles_n = pl.tiles_n;
+  p.num_spatial = pl.num_spatial; p.tiles_per_image = p.tiles_h * p.tiles_w;
+  p.Q = pl.Q; p.pairs = pl.pairs;
+  p.kchunks = pl.kchunks; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols;
+  p.resident = pl.resident; p.w_bytes = pl.w_bytes;
+  p.bias = bias; p.bias_mul = bias_mul; p.act = act;
+  p.noise = noise; p.noise_w = noise_w; p.part = part;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  cudaStream_t st = (cudaStream_t)stream;
+  return part ? launch<true>(map_x, map_w, p, pl, st) : launch<false>(map_x, map_w, p, pl, st);
+}
+
+// part as written by sg_conv3x3_pair for the same (N, H, W, Cin, Cout); style [N, 2*Cout] or null; mr [N,Cout,2];
+// ab [N,Cout,3] = (mean, rstd*(1+s0), s1) -- the coefficient layout of sg_affine_nc.
+SG_EXPORT int sg_epi_finalize_parts(const float* part, const float* style, float* mr, float* ab, int N, int H, int W,
+                                    int Cin, int Cout, float eps, void* stream) {
+  using namespace tc2;
+  Plan pl;
+  SG_REQUIRE(make_plan(N, H, W, Cin, Cout, &pl), "sg_epi_finalize_parts: shape not supported");
+  const int T = (H / TH) * (W / TW);
+  finalize_parts_kernel<<<sg_cdiv((long long)N * Cout, 128), 128, 0, (cudaStream_t)stream>>>(
+      part, style, mr, ab, N, Cout, H * W, T, pl.Q, pl.pairs, eps);
+  return sg_check_launch("sg_epi_finalize_parts");
+}

@@ -15,8 +15,14 @@ def _conv_then_epilogue(conv, epi, x, dlatent):
     """conv -> [blur] -> (+bias) -> LayerEpilogue with the bias add folded into the epilogue's first pass."""
     b_mul = conv.b_mul if conv.bias is not None else 1.0
     if conv.intermediate is None:
+        fused = epi.conv_fused_nhwc(conv, x, dlatent)
+        if fused is not None:
+            return fused
         y = conv.conv_nhwc(x, with_bias=False)
         return epi.forward_nhwc(y, dlatent, pre_bias=conv.bias, pre_bias_mul=b_mul)
+    fused = epi.blur_fused_nhwc(conv, x, dlatent)
+    if fused is not None:
+        return fused
     return epi.forward_nhwc(conv.forward_nhwc(x), dlatent)
 
 

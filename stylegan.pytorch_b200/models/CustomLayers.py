@@ -282,6 +282,41 @@ class LayerEpilogue(nn.Module):
         eps = self.top_epi.instance_norm.eps
         return _ops.Epilogue.apply(x, pre_bias, pre_bias_mul, noise, nw, style, eps, True)
 
+    def conv_fused_nhwc(self, conv, x, dlatent):
+        """conv3x3 + this epilogue with noise / LeakyReLU / InstanceNorm statistics inside the convolution kernel
+        (_ops.ConvEpilogue); None when the configuration or the shape is outside that kernel's domain."""
+        from . import _tc
+        if not self._fusable or conv.kernel_size != 3 or conv.upscale is not None or conv.downscale is not None \
+                or conv.intermediate is not None or not _tc.conv_epilogue_supported(x, conv.weight):
+            return None
+        noise_mod = self.top_epi.noise if hasattr(self.top_epi, "noise") else None
+        noise = nw = None
+        if noise_mod is not None:
+            noise = noise_mod.get_noise(x.shape[0], x.shape[1], x.shape[2], x.device)
+            nw = noise_mod.weight
+        style = self.style_mod.lin(dlatent) if self.style_mod is not None else None
+        b_mul = conv.b_mul if conv.bias is not None else 1.0
+        return _ops.ConvEpilogue.apply(x, conv.weight, conv.bias, conv.w_mul, b_mul, noise, nw, style,
+                                       self.top_epi.instance_norm.eps)
+
+    def blur_fused_nhwc(self, conv, x, dlatent):
+        """up-conv -> [1,2,1] blur -> +bias -> this epilogue, with everything after the convolution up to the
+        InstanceNorm statistics in one pass (_ops.BlurEpilogue); None outside that kernel's domain."""
+        if not self._fusable or not isinstance(conv.intermediate, BlurLayer) or not conv.intermediate.is_standard:
+            return None
+        y = conv.conv_nhwc(x, with_bias=False)
+        if not _ops.BlurEpilogue.supported(y):
+            b_mul = conv.b_mul if conv.bias is not None else 1.0
+            return self.forward_nhwc(_ops.Blur.apply(y, conv.bias, b_mul), dlatent)
+        noise_mod = self.top_epi.noise if hasattr(self.top_epi, "noise") else None
+        noise = nw = None
+        if noise_mod is not None:
+            noise = noise_mod.get_noise(y.shape[0], y.shape[1], y.shape[2], y.device)
+            nw = noise_mod.weight
+        style = self.style_mod.lin(dlatent) if self.style_mod is not None else None
+        b_mul = conv.b_mul if conv.bias is not None else 1.0
+        return _ops.BlurEpilogue.apply(y, conv.bias, b_mul, noise, nw, style, self.top_epi.instance_norm.eps)
+
     def top_epi_general(self, x):
         for name, m in self.top_epi.named_children():
             if name == "activation":

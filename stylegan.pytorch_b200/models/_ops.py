@@ -16,7 +16,8 @@ from torch.autograd.function import once_differentiable
 from . import _geom
 from ._lib import lib, ptr, stream, code, count_launch
 
-_state = {"dtype": torch.float32, "use_tc": True, "skip_param_grads": False, "fused_updown": True}
+_state = {"dtype": torch.float32, "use_tc": True, "skip_param_grads": False, "fused_updown": True, "use_pair": True,
+          "fuse_epilogue": True}
 
 
 class skip_param_grads:
@@ -713,28 +714,129 @@ class Epilogue(Function):
     def backward(ctx, g):
         z, mr, style, noise = ctx.saved_tensors
         has_bias, bias_mul, has_noise, act = ctx.cfg
-        g = _c(g)
-        N, H, W, C = z.shape
-        HW = H * W
-        dev = z.device
-        sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
-        lib.sg_epi_bwd_reduce(ptr(g), ptr(z), ptr(mr), ptr(sums), code(z.dtype), N, HW, C, stream())
-        gstyle = torch.empty((N, 2 * C), dtype=torch.float32, device=dev) if style is not None else None
-        coef = torch.empty((N, C, 4), dtype=torch.float32, device=dev)
-        lib.sg_epi_bwd_finalize(ptr(sums), ptr(mr), ptr(style), ptr(gstyle), ptr(coef), N, C, HW, stream())
-        gy = torch.empty_like(z)
-        lib.sg_epi_bwd_apply(ptr(g), ptr(z), ptr(coef), int(act), ptr(gy), code(z.dtype), N, HW, C, stream())
-        count_launch(4)
-        gb = gnw = None
-        need_b = has_bias and ctx.needs_input_grad[1]
-        need_n = has_noise and ctx.needs_input_grad[4]
-        if need_b or need_n:
-            rows = ChannelSum.apply(gy, noise if need_n else None, need_b, 1.0)
-            if need_n:
-                gnw = rows[0]
-            if need_b:
-                gb = rows[-1] * bias_mul
+        gy, gb, gnw, gstyle = _epilogue_backward(g, z, mr, style, noise, act, bias_mul,
+                                                 has_bias and ctx.needs_input_grad[1],
+                                                 has_noise and ctx.needs_input_grad[4])
         return gy, gb, None, None, gnw, gstyle, None, None
+
+
+def _epilogue_backward(g, z, mr, style, noise, act, bias_mul, need_b, need_n):
+    """Backward of StyleMod(InstanceNorm(z)) o lrelu o (+bias + noise_w*noise): g = grad wrt the epilogue output ->
+    (grad wrt the pre-activation conv output, grad bias, grad noise weight, grad style)."""
+    g = _c(g)
+    N, H, W, C = z.shape
+    HW = H * W
+    dev = z.device
+    sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
+    lib.sg_epi_bwd_reduce(ptr(g), ptr(z), ptr(mr), ptr(sums), code(z.dtype), N, HW, C, stream())
+    gstyle = torch.empty((N, 2 * C), dtype=torch.float32, device=dev) if style is not None else None
+    coef = torch.empty((N, C, 4), dtype=torch.float32, device=dev)
+    lib.sg_epi_bwd_finalize(ptr(sums), ptr(mr), ptr(style), ptr(gstyle), ptr(coef), N, C, HW, stream())
+    gy = torch.empty_like(z)
+    lib.sg_epi_bwd_apply(ptr(g), ptr(z), ptr(coef), int(act), ptr(gy), code(z.dtype), N, HW, C, stream())
+    count_launch(4)
+    gb = gnw = None
+    if need_b or need_n:
+        rows = ChannelSum.apply(gy, noise if need_n else None, need_b, 1.0)
+        if need_n:
+            gnw = rows[0]
+        if need_b:
+            gb = rows[-1] * bias_mul
+    return gy, gb, gnw, gstyle
+
+
+class ConvEpilogue(Function):
+    """conv3x3 -> LayerEpilogue with the noise add, LeakyReLU and the InstanceNorm statistics fused into the tcgen05
+    convolution's epilogue (reference CustomLayers.py:170-171 then :242-248): the convolution result is written once,
+    already activated, and the only other forward pass over it is the InstanceNorm + StyleMod affine.
+    x NHWC bf16; W [Co,Ci,3,3]; bias [Co]; noise fp32 [N,1,H,W]; noise_w [Co]; style fp32 [N,2Co]."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, scale, bias_mul, noise, noise_w, style, eps):
+        from . import _tc
+        _require_cuda(x)
+        x = _c(x)
+        if noise is not None:
+            noise = _c(noise.float())
+            assert noise.numel() == x.shape[0] * x.shape[1] * x.shape[2], "noise must be [N,1,H,W]"
+        if style is not None:
+            style = _c(style)
+        z, mr, ab = _tc.conv_epilogue_forward(x, W, scale, bias, bias_mul, noise, noise_w, style, eps)
+        N, H, Wd, C = z.shape
+        out = torch.empty_like(z)
+        lib.sg_affine_nc(ptr(z), ptr(ab), ptr(out), code(z.dtype), N, H * Wd, C, stream())
+        count_launch()
+        ctx.save_for_backward(x, W, z, mr, style, noise)
+        ctx.cfg = (scale, bias is not None, bias_mul, noise is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, W, z, mr, style, noise = ctx.saved_tensors
+        scale, has_bias, bias_mul, has_noise = ctx.cfg
+        gy, gb, gnw, gstyle = _epilogue_backward(g, z, mr, style, noise, True, bias_mul,
+                                                 has_bias and ctx.needs_input_grad[2],
+                                                 has_noise and ctx.needs_input_grad[6])
+        with torch.no_grad():
+            gx = _conv_raw(gy, W, "same", "dgrad", scale) if ctx.needs_input_grad[0] else None
+            gW = ConvWgrad.apply(x, gy, "same", scale, W.shape) if ctx.needs_input_grad[1] else None
+        return gx, gW, gb, None, None, None, gnw, gstyle, None
+
+
+class BlurEpilogue(Function):
+    """BlurLayer (+ the conv bias) -> LayerEpilogue with the blur, bias, noise add, LeakyReLU and the InstanceNorm
+    statistics in one pass (csrc/sg_blur_v2.cu: sg_blur3_epi; reference CustomLayers.py:174-180 then :242-248).
+    y NHWC bf16 = the up-convolution result WITHOUT bias."""
+
+    @staticmethod
+    def supported(y):
+        if y.dtype != torch.bfloat16 or not _state.get("fuse_epilogue", True):
+            return False
+        N, H, W, C = y.shape
+        return lib.sg_blur3_epi_slots(N, H, W, C) > 0
+
+    @staticmethod
+    def forward(ctx, y, bias, bias_mul, noise, noise_w, style, eps):
+        _require_cuda(y)
+        y = _c(y)
+        N, H, W, C = y.shape
+        dev = y.device
+        if noise is not None:
+            noise = _c(noise.float())
+            assert noise.numel() == N * H * W, "noise must be [N,1,H,W]"
+        if style is not None:
+            style = _c(style)
+        slots = lib.sg_blur3_epi_slots(N, H, W, C)
+        z = torch.empty_like(y)
+        part = torch.empty((N, slots, 2, C), dtype=torch.float32, device=dev)
+        lib.sg_blur3_epi(ptr(y), ptr(z), ptr(bias), float(bias_mul), ptr(noise),
+                         ptr(noise_w if noise is not None else None), ptr(part), N, H, W, C, stream())
+        mr = torch.empty((N, C, 2), dtype=torch.float32, device=dev)
+        ab = torch.empty((N, C, 3), dtype=torch.float32, device=dev)
+        lib.sg_epi_finalize_slots(ptr(part), slots, ptr(style), ptr(mr), ptr(ab), N, C, H * W, float(eps), stream())
+        out = torch.empty_like(y)
+        lib.sg_affine_nc(ptr(z), ptr(ab), ptr(out), code(y.dtype), N, H * W, C, stream())
+        count_launch(3)
+        ctx.save_for_backward(z, mr, style, noise)
+        ctx.cfg = (bias is not None, bias_mul, noise is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        z, mr, style, noise = ctx.saved_tensors
+        has_bias, bias_mul, has_noise = ctx.cfg
+        gp, gb, gnw, gstyle = _epilogue_backward(g, z, mr, style, noise, True, bias_mul,
+                                                 has_bias and ctx.needs_input_grad[1],
+                                                 has_noise and ctx.needs_input_grad[4])
+        gy = None
+        if ctx.needs_input_grad[0]:
+            N, H, W, C = z.shape
+            gy = torch.empty_like(gp)                       # the blur is self-adjoint
+            lib.sg_blur3(ptr(gp), ptr(gy), None, 1.0, code(gp.dtype), N, H, W, C, stream())
+            count_launch()
+        return gy, gb, None, None, gnw, gstyle, None
 
 
 class ToRgb(Function):

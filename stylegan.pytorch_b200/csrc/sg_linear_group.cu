@@ -1,0 +1,238 @@
+// Grouped dense layers: G independent affine maps  y_g[B,O_g] = scale_g * x_g[B,I] W_g[O_g,I]^T + bias_g * bmul_g  in ONE
+// launch, with their data gradient and weight/bias gradients as one launch each.
+//
+// reference call sites: the 2 x (number of synthesis layers) StyleMod affines of one Generator forward
+// (models/CustomLayers.py:203-216: EqualizedLinear(latent, 2C) applied to dlatents_in_range[:, l]) -- 14 at 256x256, 18 at
+// 1024x1024 -- which the reference (and round 1 of this engine) evaluates as 14 separate tiny GEMMs (38 us each on a
+// B200, latency-bound: 16-128 blocks, one dependent global-load chain per warp).  All of them depend only on the dlatents,
+// so they run before the synthesis network starts; their gradients arrive together at the end of its backward.
+// fp32 throughout (these feed the fp32-parity path as well): CUDA-core FMAs, all global loads of a warp issued up front.
+#include "sg_common.cuh"
+#include "../../include/sgb200.h"
+#include <mutex>
+
+namespace {
+
+constexpr int LG_B = 32;        // batch rows per launch (callers with more rows loop)
+constexpr int LG_OPB = 16;      // outputs per block (2 per warp, 8 warps)
+
+// One table row per group (device memory, 8 x int64): pointers as integers, floats as their bit patterns.
+struct LinGroup {
+  long long x;        // const float*  [B, I] with row stride ldx
+  long long ldx;
+  long long W;        // const float*  [O, I]
+  long long bias;     // const float*  [O] or 0
+  long long y;        // float*        [B, O]   (fwd: output; bwd: the incoming gradient gy)
+  long long O;
+  long long scales;   // low 32 bits: scale, high 32 bits: bias_mul
+  long long blk0;     // first block of this group in the launch (prefix sum of ceil(O / outputs-per-block))
+};
+
+__device__ __forceinline__ float lo_f(long long v) { return __int_as_float((int)(v & 0xffffffffll)); }
+__device__ __forceinline__ float hi_f(long long v) { return __int_as_float((int)((unsigned long long)v >> 32)); }
+
+__device__ __forceinline__ int find_group(const LinGroup* __restrict__ tab, int G, int blk) {
+  int g = 0;
+  while (g + 1 < G && (int)tab[g + 1].blk0 <= blk) ++g;
+  return g;
+}
+
+// ---- forward: block = 16 outputs of one group; x_g staged once in shared memory -------------------------------------------
+template <int IV>   // I = 128 * IV floats (IV float4 per lane)
+__global__ void __launch_bounds__(256) lingroup_fwd_kernel(const LinGroup* __restrict__ tab, int G, int B, int act) {
+  extern __shared__ float xs[];                        // [B][I]
+  constexpr int I = 128 * IV;
+  const int g = find_group(tab, G, blockIdx.x);
+  const LinGroup t = tab[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int O = (int)t.O;
+  const int o0 = ((int)blockIdx.x - (int)t.blk0) * LG_OPB + warp * 2;
+  // this warp's two weight rows: every load of the warp is in flight before anything is consumed
+  const float* Wp = reinterpret_cast<const float*>(t.W);
+  float4 w[2][IV];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int o = o0 + r < O ? o0 + r : O - 1;
+#pragma unroll
+    for (int v = 0; v < IV; ++v) w[r][v] = *reinterpret_cast<const float4*>(Wp + (size_t)o * I + v * 128 + lane * 4);
+  }
+  const float* xp = reinterpret_cast<const float*>(t.x);
+  for (int i = threadIdx.x; i < B * (I / 4); i += blockDim.x) {
+    const int b = i / (I / 4), c = i % (I / 4);
+    reinterpret_cast<float4*>(xs)[i] = *reinterpret_cast<const float4*>(xp + (size_t)b * t.ldx + c * 4);
+  }
+  __syncthreads();
+  const float scale = lo_f(t.scales), bmul = hi_f(t.scales);
+  const float* bp = reinterpret_cast<const float*>(t.bias);
+  float* yp = reinterpret_cast<float*>(t.y);
+  for (int b0 = 0; b0 < B; b0 += 8) {                  // 8 batch rows x 2 outputs = 16 accumulators at a time
+    float acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.f;
+#pragma unroll
+    for (int v = 0; v < IV; ++v) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)(b0 + j) * I + v * 128 + lane * 4);
+        acc[j][0] = fmaf(xv.x, w[0][v].x, fmaf(xv.y, w[0][v].y, fmaf(xv.z, w[0][v].z, fmaf(xv.w, w[0][v].w, acc[j][0]))));
+        acc[j][1] = fmaf(xv.x, w[1][v].x, fmaf(xv.y, w[1][v].y, fmaf(xv.z, w[1][v].z, fmaf(xv.w, w[1][v].w, acc[j][1]))));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float s = sg_warp_sum(acc[j][r]);
+        if (lane == 0 && o0 + r < O && b0 + j < B) {
+          float v = s * scale + (bp ? bp[o0 + r] * bmul : 0.f);
+          yp[(size_t)(b0 + j) * O + o0 + r] = act ? sg_lrelu(v) : v;
+        }
+      }
+    }
+  }
+}
+
+// ---- data gradient: gx_g[b, i] = scale_g * sum_o gy_g[b, o] W_g[o, i];  block = (group, 64 input columns) ----------------
+// gx is written with row stride ldx into the tensor x points at (for the StyleMod group: the gradient of dlatents[:, l]).
+__global__ void __launch_bounds__(256) lingroup_dgrad_kernel(const LinGroup* __restrict__ tab, int G, int B, int I,
+                                                             int accumulate) {
+  __shared__ float gs[LG_B][65];                       // gy chunk [b][o within chunk of 64]
+  const int col_blocks = I / 64;
+  const int g = blockIdx.x / col_blocks, cb = blockIdx.x % col_blocks;
+  const LinGroup t = tab[g];
+  const int O = (int)t.O;
+  const int i = cb * 64 + (threadIdx.x & 63), bq = threadIdx.x >> 6;      // 4 batch quarters of 8 rows
+  const float* Wp = reinterpret_cast<const float*>(t.W);
+  const float* gyp = reinterpret_cast<const float*>(t.y);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int oc = 0; oc < O; oc += 64) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < LG_B * 64; e += blockDim.x) {
+      const int b = e >> 6, o = e & 63;
+      gs[b][o] = (b < B && oc + o < O) ? gyp[(size_t)b * O + oc + o] : 0.f;
+    }
+    __syncthreads();
+    const int on = min(64, O - oc);
+    float wv[8];
+    for (int o = 0; o < on; o += 8) {                  // 8 independent weight loads per thread in flight
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = (o + u < on) ? Wp[(size_t)(oc + o + u) * I + i] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gs[bq * 8 + j][o + u], wv[u], acc[j]);
+    }
+  }
+  const float scale = lo_f(t.scales);
+  float* gx = reinterpret_cast<float*>(t.x);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = bq * 8 + j;
+    if (b < B) {
+      float* d = gx + (size_t)b * t.ldx + i;
+      *d = (accumulate ? *d : 0.f) + acc[j] * scale;
+    }
+  }
+}
+
+// ---- weight / bias gradient: gW_g[o, i] = scale_g * sum_b gy_g[b, o] x_g[b, i]; gb_g[o] = bmul_g * sum_b gy_g[b, o] --------
+// table rows here: x = activations, W = gW (output), bias = gb (output or 0), y = gy.  block = 8 output rows of one group.
+template <int IV>
+__global__ void __launch_bounds__(256) lingroup_wgrad_kernel(const LinGroup* __restrict__ tab, int G, int B) {
+  extern __shared__ float xs[];                        // [B][I]
+  constexpr int I = 128 * IV;
+  __shared__ float gys[LG_B][8];
+  const int g = find_group(tab, G, blockIdx.x);
+  const LinGroup t = tab[g];
+  const int O = (int)t.O;
+  const int o0 = ((int)blockIdx.x - (int)t.blk0) * 8;
+  const float* xp = reinterpret_cast<const float*>(t.x);
+  const float* gyp = reinterpret_cast<const float*>(t.y);
+  for (int i = threadIdx.x; i < B * (I / 4); i += blockDim.x) {
+    const int b = i / (I / 4), c = i % (I / 4);
+    reinterpret_cast<float4*>(xs)[i] = *reinterpret_cast<const float4*>(xp + (size_t)b * t.ldx + c * 4);
+  }
+  for (int e = threadIdx.x; e < LG_B * 8; e += blockDim.x) {
+    const int b = e >> 3, r = e & 7;
+    gys[b][r] = (b < B && o0 + r < O) ? gyp[(size_t)b * O + o0 + r] : 0.f;
+  }
+  __syncthreads();
+  const float scale = lo_f(t.scales), bmul = hi_f(t.scales);
+  float* gW = reinterpret_cast<float*>(t.W);
+  // thread owns I/256 float2... simpler: each thread handles columns c = tid*4 .. +3 for IV == 4 (I = 512: 128 threads x 4)
+  for (int c = threadIdx.x * 4; c < I; c += blockDim.x * 4) {
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)b * I + c);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float gv = gys[b][r];
+        acc[r][0] = fmaf(gv, xv.x, acc[r][0]); acc[r][1] = fmaf(gv, xv.y, acc[r][1]);
+        acc[r][2] = fmaf(gv, xv.z, acc[r][2]); acc[r][3] = fmaf(gv, xv.w, acc[r][3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (o0 + r < O)
+        *reinterpret_cast<float4*>(gW + (size_t)(o0 + r) * I + c) =
+            make_float4(acc[r][0] * scale, acc[r][1] * scale, acc[r][2] * scale, acc[r][3] * scale);
+  }
+  float* gb = reinterpret_cast<float*>(t.bias);
+  if (gb && threadIdx.x < 8 && o0 + (int)threadIdx.x < O) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += gys[b][threadIdx.x];
+    gb[o0 + threadIdx.x] = s * bmul;
+  }
+}
+
+}  // namespace
+
+SG_EXPORT int sg_lingroup_rows(void) { return 8; }   // int64 words per table row
+
+// blocks of the forward / weight-gradient launch for one group of O outputs (the caller builds the blk0 prefix sums)
+SG_EXPORT int sg_lingroup_fwd_blocks(int O) { return (O + LG_OPB - 1) / LG_OPB; }
+SG_EXPORT int sg_lingroup_wgrad_blocks(int O) { return (O + 7) / 8; }
+
+SG_EXPORT int sg_lingroup_supported(int B, int I) { return (B >= 1 && B <= LG_B && (I == 512 || I == 256 || I == 128)) ? 1 : 0; }
+
+SG_EXPORT int sg_lingroup_fwd(const void* table, int G, int total_blocks, int B, int I, int act, void* stream) {
+  SG_REQUIRE(sg_lingroup_supported(B, I), "sg_lingroup_fwd: B must be <= 32 and I in {128, 256, 512}");
+  const LinGroup* tab = reinterpret_cast<const LinGroup*>(table);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)B * I * sizeof(float);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(lingroup_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lingroup_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  });
+  if (I == 512) lingroup_fwd_kernel<4><<<total_blocks, 256, smem, st>>>(tab, G, B, act);
+  else if (I == 256) lingroup_fwd_kernel<2><<<total_blocks, 256, smem, st>>>(tab, G, B, act);
+  else lingroup_fwd_kernel<1><<<total_blocks, 256, smem, st>>>(tab, G, B, act);
+  return sg_check_launch("sg_lingroup_fwd");
+}
+
+SG_EXPORT int sg_lingroup_dgrad(const void* table, int G, int B, int I, int accumulate, void* stream) {
+  SG_REQUIRE(sg_lingroup_supported(B, I), "sg_lingroup_dgrad: B must be <= 32 and I in {128, 256, 512}");
+  lingroup_dgrad_kernel<<<G * (I / 64), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const LinGroup*>(table), G, B, I,
+                                                                      accumulate);
+  return sg_check_launch("sg_lingroup_dgrad");
+}
+
+SG_EXPORT int sg_lingroup_wgrad(const void* table, int G, int total_blocks, int B, int I, void* stream) {
+  SG_REQUIRE(sg_lingroup_supported(B, I), "sg_lingroup_wgrad: B must be <= 32 and I in {128, 256, 512}");
+  const LinGroup* tab = reinterpret_cast<const LinGroup*>(table);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)B * I * sizeof(float);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(lingroup_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  });
+  if (I == 512) lingroup_wgrad_kernel<4><<<total_blocks, 256, smem, st>>>(tab, G, B);
+  else if (I == 256) lingroup_wgrad_kernel<2><<<total_blocks, 256, smem, st>>>(tab, G, B);
+  else lingroup_wgrad_kernel<1><<<total_blocks, 256, smem, st>>>(tab, G, B);
+  return sg_check_launch("sg_lingroup_wgrad");
+}

@@ -278,9 +278,20 @@ class LayerEpilogue(nn.Module):
         if noise_mod is not None:
             noise = noise_mod.get_noise(x.shape[0], x.shape[1], x.shape[2], x.device)
             nw = noise_mod.weight
-        style = self.style_mod.lin(dlatent) if self.style_mod is not None else None
+        style = self._take_style(dlatent)
         eps = self.top_epi.instance_norm.eps
         return _ops.Epilogue.apply(x, pre_bias, pre_bias_mul, noise, nw, style, eps, True)
+
+    def _take_style(self, dlatent):
+        """The StyleMod affine of this layer: precomputed for the whole synthesis pass by GSynthesis (one grouped launch,
+        _ops.StyleAffines) or evaluated here."""
+        if self.style_mod is None:
+            return None
+        pre = getattr(self, "_style_pre", None)
+        if pre is not None:
+            self._style_pre = None
+            return pre
+        return self.style_mod.lin(dlatent)
 
     def conv_fused_nhwc(self, conv, x, dlatent):
         """conv3x3 + this epilogue with noise / LeakyReLU / InstanceNorm statistics inside the convolution kernel
@@ -294,7 +305,7 @@ class LayerEpilogue(nn.Module):
         if noise_mod is not None:
             noise = noise_mod.get_noise(x.shape[0], x.shape[1], x.shape[2], x.device)
             nw = noise_mod.weight
-        style = self.style_mod.lin(dlatent) if self.style_mod is not None else None
+        style = self._take_style(dlatent)
         b_mul = conv.b_mul if conv.bias is not None else 1.0
         return _ops.ConvEpilogue.apply(x, conv.weight, conv.bias, conv.w_mul, b_mul, noise, nw, style,
                                        self.top_epi.instance_norm.eps)
@@ -313,7 +324,7 @@ class LayerEpilogue(nn.Module):
         if noise_mod is not None:
             noise = noise_mod.get_noise(y.shape[0], y.shape[1], y.shape[2], y.device)
             nw = noise_mod.weight
-        style = self.style_mod.lin(dlatent) if self.style_mod is not None else None
+        style = self._take_style(dlatent)
         b_mul = conv.b_mul if conv.bias is not None else 1.0
         return _ops.BlurEpilogue.apply(y, conv.bias, b_mul, noise, nw, style, self.top_epi.instance_norm.eps)
 

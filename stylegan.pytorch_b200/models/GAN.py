@@ -112,6 +112,25 @@ class GSynthesis(nn.Module):
         lo = self.to_rgb[j_lo]
         return _ops.ToRgb.apply(x_hi, hi.weight, hi.bias, hi.w_mul, a_hi, x_lo, lo.weight, lo.bias, lo.w_mul, a_lo)
 
+    def _precompute_styles(self, dl, n_blocks):
+        """All StyleMod affines this pass will need, in one grouped launch, handed to their LayerEpilogues."""
+        epis = [(0, self.init_block.epi1), (1, self.init_block.epi2)]
+        for i in range(n_blocks):
+            epis += [(2 * (i + 1), self.blocks[i].epi1), (2 * (i + 1) + 1, self.blocks[i].epi2)]
+        epis = [(l, e) for l, e in epis if e.style_mod is not None and e._fusable]
+        if not epis or dl.dim() != 3 or not _ops.StyleAffines.supported(dl):
+            return
+        if not dl.is_contiguous():
+            dl = dl.contiguous()
+        params, cfg = [], []
+        for _, e in epis:
+            lin = e.style_mod.lin
+            params += [lin.weight, lin.bias]
+            cfg.append((lin.w_mul, lin.b_mul if lin.bias is not None else 1.0))
+        styles = _ops.StyleAffines.apply(dl, tuple(l for l, _ in epis), tuple(cfg), *params)
+        for (_, e), s in zip(epis, styles):
+            e._style_pre = s
+
     def forward(self, dlatents_in, depth=0, alpha=0., labels_in=None):
         """dlatents_in [B, num_layers, dlatent] -> images [B, C, R, R] float32 (NCHW)."""
         assert depth < self.depth, "Requested output depth cannot be produced"
@@ -119,6 +138,7 @@ class GSynthesis(nn.Module):
             return _host_facade.call(self, dlatents_in, depth=depth, alpha=alpha, labels_in=labels_in)
         _ops._require_cuda(dlatents_in)
         dl = dlatents_in.float()
+        self._precompute_styles(dl, len(self.blocks) if self.structure == 'fixed' else depth)
         if self.structure == 'fixed':
             x = self.init_block.forward_nhwc(dl[:, 0:2])
             for i, block in enumerate(self.blocks):

@@ -548,6 +548,102 @@ class LinearWgrad(Function):
         raise RuntimeError("sgb200: LinearWgrad is not differentiable")
 
 
+def _pack_scales(scale, bias_mul):
+    import struct
+    return struct.unpack("<q", struct.pack("<ff", float(scale), float(bias_mul)))[0]
+
+
+def _lingroup_table(rows, device):
+    """rows: list of 8 python ints per group -> int64 device tensor (one small host-to-device copy)."""
+    t = torch.tensor(rows, dtype=torch.int64).reshape(-1, 8)
+    return t.to(device, non_blocking=True)
+
+
+class StyleAffines(Function):
+    """All StyleMod affines of one synthesis pass in one launch (csrc/sg_linear_group.cu; reference
+    CustomLayers.py:203-216 evaluates them one by one inside each LayerEpilogue):
+        styles[l] = w_mul_l * dlatents[:, idx_l] W_l^T + b_l * b_mul_l          (fp32, [B, 2C_l])
+    backward: one launch for the gradient wrt dlatents and one for all weight + bias gradients.
+    args: dlatents [B, L, D] fp32 contiguous, idx (tuple of layer indices), cfg (tuple of (w_mul, b_mul)), then
+    W_0, b_0, W_1, b_1, ... (b may be None)."""
+
+    @staticmethod
+    def supported(dlatents):
+        B, L, D = dlatents.shape
+        return dlatents.dtype == torch.float32 and bool(lib.sg_lingroup_supported(min(B, 32), D))
+
+    @staticmethod
+    def forward(ctx, dlatents, idx, cfg, *params):
+        _require_cuda(dlatents)
+        dl = _c(dlatents)
+        B, L, D = dl.shape
+        dev = dl.device
+        Ws, bs = params[0::2], params[1::2]
+        outs = [torch.empty((B, W.shape[0]), dtype=torch.float32, device=dev) for W in Ws]
+        for b0 in range(0, B, 32):
+            nb = min(32, B - b0)
+            rows, blk = [], 0
+            for l, W, b, (w_mul, b_mul), y in zip(idx, Ws, bs, cfg, outs):
+                O = W.shape[0]
+                rows.append([dl.data_ptr() + 4 * (b0 * L * D + l * D), L * D, W.data_ptr(),
+                             b.data_ptr() if b is not None else 0, y.data_ptr() + 4 * b0 * O, O,
+                             _pack_scales(w_mul, b_mul), blk])
+                blk += lib.sg_lingroup_fwd_blocks(O)
+            tab = _lingroup_table(rows, dev)
+            lib.sg_lingroup_fwd(ptr(tab), len(rows), blk, nb, D, 0, stream())
+            count_launch()
+        ctx.save_for_backward(dl, *[p for p in params if p is not None])
+        ctx.meta = (idx, cfg, [b is not None for b in bs])
+        ctx.mark_non_differentiable()
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gys):
+        idx, cfg, has_b = ctx.meta
+        saved = ctx.saved_tensors
+        dl = saved[0]
+        it = iter(saved[1:])
+        Ws, bs = [], []
+        for hb in has_b:
+            Ws.append(next(it))
+            bs.append(next(it) if hb else None)
+        B, L, D = dl.shape
+        dev = dl.device
+        gys = [(_c(g) if g is not None else torch.zeros((B, W.shape[0]), dtype=torch.float32, device=dev))
+               for g, W in zip(gys, Ws)]
+        gdl = None
+        if ctx.needs_input_grad[0]:
+            assert len(set(idx)) == len(idx), "each dlatent layer feeds one StyleMod"
+            gdl = torch.empty_like(dl) if len(idx) == L else torch.zeros_like(dl)
+            for b0 in range(0, B, 32):
+                nb = min(32, B - b0)
+                rows = []
+                for l, W, (w_mul, _), g in zip(idx, Ws, cfg, gys):
+                    O = W.shape[0]
+                    rows.append([gdl.data_ptr() + 4 * (b0 * L * D + l * D), L * D, W.data_ptr(), 0,
+                                 g.data_ptr() + 4 * b0 * O, O, _pack_scales(w_mul, 1.0), 0])
+                tab = _lingroup_table(rows, dev)
+                lib.sg_lingroup_dgrad(ptr(tab), len(rows), nb, D, 0, stream())
+                count_launch()
+        grads = [None] * (2 * len(Ws))
+        if _want_params() and any(ctx.needs_input_grad[3:]):
+            assert B <= 32, "sgb200: grouped StyleMod weight gradients are implemented for batch <= 32 per GPU"
+            rows, blk = [], 0
+            for k, (l, W, b, (w_mul, b_mul), g) in enumerate(zip(idx, Ws, bs, cfg, gys)):
+                O = W.shape[0]
+                gW = torch.empty_like(W)
+                gb = torch.empty_like(b) if b is not None else None
+                grads[2 * k], grads[2 * k + 1] = gW, gb
+                rows.append([dl.data_ptr() + 4 * l * D, L * D, gW.data_ptr(), gb.data_ptr() if gb is not None else 0,
+                             g.data_ptr(), O, _pack_scales(w_mul, b_mul), blk])
+                blk += lib.sg_lingroup_wgrad_blocks(O)
+            tab = _lingroup_table(rows, dev)
+            lib.sg_lingroup_wgrad(ptr(tab), len(rows), blk, B, D, stream())
+            count_launch()
+        return (gdl, None, None, *grads)
+
+
 class PixelNorm(Function):
     @staticmethod
     def forward(ctx, x, eps):

@@ -195,3 +195,41 @@ def test_fused_blur_epilogue_function_equals_unfused(N, R, C):
     s = style0.cpu().view(N, 2, C, 1, 1)
     ref = zn * (s[:, 0] + 1.0) + s[:, 1]
     assert rel(res[0][0].float().permute(0, 3, 1, 2), ref) < 1.2e-2
+
+
+@pytest.mark.parametrize("B,L,D", [(4, 6, 512), (32, 14, 512), (40, 4, 512), (8, 4, 128)])
+def test_grouped_style_affines_equal_separate_linears(B, L, D):
+    """_ops.StyleAffines (one launch for all StyleMod affines, one for their dgrad, one for their wgrad) against the
+    per-layer _ops.Linear and against plain torch."""
+    from models import _ops
+    torch.manual_seed(5)
+    chans = [512, 512, 256, 128, 64, 32, 16][: max(1, L // 2)]
+    idx = tuple(range(0, 2 * len(chans)))[:L]
+    Os = [2 * chans[i // 2] for i in idx]
+    dl0 = torch.randn(B, L, D, device=DEV)
+    Ws = [torch.nn.Parameter(torch.randn(O, D, device=DEV)) for O in Os]
+    bs = [torch.nn.Parameter(torch.randn(O, device=DEV)) for O in Os]
+    cfg = tuple((D ** -0.5, 1.0) for _ in Os)
+    gouts = [torch.randn(B, O, device=DEV) for O in Os]
+    params = [p for pair in zip(Ws, bs) for p in pair]
+    res = []
+    for grouped in (True, False):
+        dl = dl0.clone().requires_grad_(True)
+        if grouped:
+            outs = _ops.StyleAffines.apply(dl, idx, cfg, *params)
+        else:
+            outs = [_ops.Linear.apply(dl[:, l].contiguous(), W, b, c[0], c[1], False) for l, W, b, c in zip(idx, Ws, bs, cfg)]
+        if B > 32 and grouped:
+            with _ops.skip_param_grads():
+                grads = torch.autograd.grad(outs, [dl], gouts)
+        else:
+            grads = torch.autograd.grad(outs, [dl] + (params if B <= 32 else []), gouts)
+        res.append((list(outs), list(grads)))
+    torch.cuda.synchronize()
+    for a, b in zip(res[0][0], res[1][0]):
+        assert rel(a, b) < 1e-5
+    for a, b in zip(res[0][1], res[1][1]):
+        assert rel(a, b) < 1e-5
+    for l, W, b, o in zip(idx, Ws, bs, res[0][0]):
+        ref = dl0[:, l].double() @ (W.double() * D ** -0.5).t() + b.double()
+        assert rel(o, ref) < 1e-5

@@ -148,22 +148,38 @@ def make_gan(res, precision, device, seed):
 
 
 def northstar_kernel_roofline(batch, res, ch, iters=20):
-    """The fused 3x3 synthesis conv (blocks[-1].conv1: ch->ch at res x res), timed alone with CUDA events."""
+    """The fused 3x3 synthesis conv (blocks[-1].conv1: ch->ch at res x res) timed alone with CUDA events: the CTA-pair
+    tcgen05 kernel with bias, noise, LeakyReLU and the InstanceNorm statistics in its epilogue (csrc/sg_conv_pair_tc.cu);
+    falls back to the single-CTA kernel (bias + LeakyReLU only) where the pair kernel does not cover the shape."""
     import torch
     from models import _tc
     from models._lib import lib, ptr, stream
-    if not lib.sg_conv3x3_tc_supported(batch, res, res, ch, ch):
-        return None
     dev = "cuda"
+    pair = bool(lib.sg_conv3x3_pair_supported(batch, res, res, ch, ch))
+    if not pair and not lib.sg_conv3x3_tc_supported(batch, res, res, ch, ch):
+        return None
     x = torch.randn(batch, res, res, ch, device=dev).bfloat16()
     W = torch.nn.Parameter(torch.randn(ch, ch, 3, 3, device=dev))
     b = torch.randn(ch, device=dev)
     y = torch.empty_like(x)
     E = _tc.tc_weight(W, "fwd", 0.05)
     st = stream()
+    if pair:
+        noise = torch.randn(batch, 1, res, res, device=dev)
+        nw = torch.randn(ch, device=dev)
+        part = torch.empty(batch, lib.sg_conv3x3_pair_slots(batch, res, res, ch, ch), 2, ch, device=dev)
 
-    def run():
-        lib.sg_conv3x3_tc(ptr(x), ptr(E), ptr(y), ptr(b), 1.0, 1, batch, res, res, ch, ch, st)
+        def run():
+            lib.sg_conv3x3_pair(ptr(x), ptr(E), ptr(y), ptr(b), 1.0, 1, ptr(noise), ptr(nw), ptr(part), batch, res, res,
+                                ch, ch, st)
+        name = "conv3x3_pair_kernel<stats> %d->%d @%dx%d N=%d (cta_group::2; fused bias + noise + LeakyReLU + " \
+               "InstanceNorm partial sums)" % (ch, ch, res, res, batch)
+        extra_bytes = noise.numel() * 4 + part.numel() * 4
+    else:
+        def run():
+            lib.sg_conv3x3_tc(ptr(x), ptr(E), ptr(y), ptr(b), 1.0, 1, batch, res, res, ch, ch, st)
+        name = "conv3x3_tc_kernel %d->%d @%dx%d N=%d (fused bias+LeakyReLU)" % (ch, ch, res, res, batch)
+        extra_bytes = 0
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -178,23 +194,24 @@ def northstar_kernel_roofline(batch, res, ch, iters=20):
     flops = 2.0 * batch * res * res * ch * ch * 9
     pk, how = peaks()
     ach = flops / (ms * 1e-3) / 1e12
-    alg_bytes = 2.0 * batch * res * res * ch * 2 + 9 * ch * ch * 2
-    return {"bound": "tensor", "kernel": "conv3x3_tc_kernel %d->%d @%dx%d N=%d (fused bias+LeakyReLU)" % (ch, ch, res, res, batch),
+    alg_bytes = 2.0 * batch * res * res * ch * 2 + 9 * ch * ch * 2 + extra_bytes
+    return {"bound": "tensor", "kernel": name,
             "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4),
             "peak_source": how + " (burst cuBLAS bf16; kernel timed alone)", "ms_per_launch": round(ms, 4),
             "algorithmic_gflop_per_launch": round(flops / 1e9, 1),
+            "algorithmic_bytes_per_launch": int(alg_bytes),
             "hbm_gbs_algorithmic": round(alg_bytes / (ms * 1e-3) / 1e9, 1),
-            **northstar_traffic(batch, res, ch)}
+            **northstar_traffic(batch, res, ch, "pair" if pair else "conv3x3_tc")}
 
 
-def northstar_traffic(batch, res, ch):
+def northstar_traffic(batch, res, ch, kernel=""):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the north-star kernel from the committed
     `ncu --set full` capture (profiles/northstar_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep);
     null when no capture exists for this shape."""
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "northstar_traffic.json")))
         for r in rec["captures"]:
-            if (r["batch"], r["res"], r["ch"]) == (batch, res, ch):
+            if (r["batch"], r["res"], r["ch"]) == (batch, res, ch) and kernel in r["kernel"]:
                 return {"traffic": r["dram_bytes"], "traffic_unit": "bytes/launch", "traffic_source": r["source"]}
     except Exception:
         pass
@@ -491,6 +508,7 @@ def main():
                                       "EMA, style mixing, truncation) %dx%d depth %d alpha 0.5" % (R, R, depth),
                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                           "shared_real_pass": bool(Losses.LogisticGAN.shared_real_pass),
+                          "cuda_graphs": bool(sg.use_cuda_graphs) and any(e.graph is not None for e in sg._graphs.entries.values()),
                           "l2": "per-step activations (GBs) exceed the 126 MB L2; no explicit flush"},
                "e2e": {"value": round(e2e, 2), "unit": "images/sec", "ms_per_step": round(ms_e2e / args.steps, 3),
                        "h2d_bytes_per_step": B * 3 * R * R * 4 + B * 512 * 4, "d2h_bytes_per_step": 8},

@@ -122,6 +122,14 @@ int sg_wgrad3x3_tc_supported(int N, int H, int W, int Cin, int Cout);
 int sg_wgrad3x3_tc_splits(int N, int H, int W, int Cin, int Cout);
 int sg_wgrad3x3_tc(const void* x, const void* dy, float* part, int N, int H, int W, int Cin, int Cout, void* stream);
 
+/* Second-generation weight gradient (csrc/sg_wgrad2_tc.cu): every MMA is 128 x 192 x 16 -- N = the three vertical taps
+ * of one 64-channel block of x (one halo box read as three 2048-byte-shifted MN-major blocks), M = two 64-channel
+ * blocks of dy, or for Cout == 64 two horizontally shifted copies of dy.  Same `part` layout as sg_wgrad3x3_tc with
+ * S = sg_wgrad3x3_v2_splits.  Covers Cin % 64 == 0 and Cout == 64 or Cout % 128 == 0. */
+int sg_wgrad3x3_v2_supported(int N, int H, int W, int Cin, int Cout);
+int sg_wgrad3x3_v2_splits(int N, int H, int W, int Cin, int Cout);
+int sg_wgrad3x3_v2(const void* x, const void* dy, float* part, int N, int H, int W, int Cin, int Cout, void* stream);
+
 /* tcgen05/TMA weight gradient of the up/down layers in the tap-merged form (csrc/sg_wgradud_tc.cu): part
  * [S][16][Cout][Cin] float32 (tap order of the layer's table), reduced onto the 3x3 parameter by sg_wprep_bwd with the
  * coefficient table of models/_geom.py (transpose=1).  H, W = low-resolution grid. */
@@ -147,6 +155,9 @@ int sg_pad_crop_nhwc(const void* src, void* dst, int dtype, int N, int hs, int w
                      void* stream);
 /* out = a*x + b*y (y may be NULL): fade-in lerps GAN.py:202,427,586; scaling. */
 int sg_axpby(const void* x, const void* y, void* out, float a, float b, long long n, int dtype, void* stream);
+/* same with (a, b) = (ab[0], ab[1]) read from device memory: per-step scalars (the fade-in alpha, models/GAN.py:202,
+ * 427, 588) must not be baked into a captured CUDA graph */
+int sg_axpby_dev(const void* x, const void* y, void* out, const float* ab, long long n, int dtype, void* stream);
 /* LeakyReLU(0.2) backward from the activation output (GAN.py:68,151,347). */
 int sg_lrelu_bwd(const void* g, const void* ref, void* gx, long long n, int dtype, void* stream);
 int sg_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, void* stream);
@@ -181,6 +192,11 @@ int sg_dlatents(const float* w1, const float* w2, const float* avg, float* out, 
                 float psi, int trunc_cutoff, void* stream);
 int sg_dlatents_bwd(const float* g, float* gw1, float* gw2, int B, int L, int D, int mix_cutoff, float psi,
                     int trunc_cutoff, int has_trunc, void* stream);
+/* the style-mixing cut-off (host RNG draw, GAN.py:287-288) read from device memory, for CUDA-graph replay */
+int sg_dlatents_dev(const float* w1, const float* w2, const float* avg, float* out, int B, int L, int D,
+                    const int* mix_cutoff, float psi, int trunc_cutoff, void* stream);
+int sg_dlatents_bwd_dev(const float* g, float* gw1, float* gw2, int B, int L, int D, const int* mix_cutoff, float psi,
+                        int trunc_cutoff, int has_trunc, void* stream);
 
 /* ---- LayerEpilogue: NoiseLayer + LeakyReLU + InstanceNorm2d + StyleMod, CustomLayers.py:191-248 ---------------- */
 int sg_epi_act_stats(const void* y, const float* bias, float bias_mul, const float* noise, const float* noise_w,
@@ -225,6 +241,8 @@ int sg_adam_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float
 int sg_ema_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float ema_beta, void* stream);
 /* NoiseLayer's torch.randn, CustomLayers.py:193 (Philox4x32-10 + Box-Muller) */
 int sg_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream);
+int sg_randn_dev(float* out, long long n, unsigned long long seed, const unsigned long long* base,
+                 unsigned long long delta, void* stream);
 
 #ifdef __cplusplus
 }

@@ -92,7 +92,9 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
-__global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset) {
+__global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                             const unsigned long long* __restrict__ base_dev = nullptr) {
+  if (base_dev) offset += *base_dev;                       // Philox counter base from device memory (CUDA-graph replay)
   const long long nq = (n + 3) / 4;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
     unsigned long long ctr = offset + (unsigned long long)q;
@@ -152,4 +154,12 @@ SG_EXPORT int sg_ema_multi(const SgTensorEntry* table_dev, int T, int total_chun
 SG_EXPORT int sg_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream) {
   randn_kernel<<<sg_grid_1d((n + 3) / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
   return sg_check_launch("sg_randn");
+}
+
+// counter = *base (device memory) + delta: the same stream of numbers as sg_randn with offset = *base + delta
+SG_EXPORT int sg_randn_dev(float* out, long long n, unsigned long long seed, const unsigned long long* base,
+                           unsigned long long delta, void* stream) {
+  SG_REQUIRE(base != nullptr, "sg_randn_dev: counter pointer missing");
+  randn_kernel<<<sg_grid_1d((n + 3) / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(out, n, seed, delta, base);
+  return sg_check_launch("sg_randn_dev");
 }

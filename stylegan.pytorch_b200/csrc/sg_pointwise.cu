@@ -118,8 +118,9 @@ __global__ void blur3_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, 
 // ---------------------------------------------------------------------------------------------------------
 template <class T>
 __global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, float a, float b,
-                             long long n) {
+                             long long n, const float* __restrict__ ab_dev = nullptr) {
   using V = SgVec<T>;
+  if (ab_dev) { a = ab_dev[0]; b = y ? ab_dev[1] : 0.f; }      // coefficients from device memory (CUDA-graph replay)
   const long long nv = n / V::N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (long long)gridDim.x * blockDim.x) {
@@ -704,7 +705,8 @@ __global__ void plane_sum_final_kernel(const float* __restrict__ part, float* __
 // ---------------------------------------------------------------------------------------------------------
 __global__ void dlatents_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
                                 const float* __restrict__ avg, float* __restrict__ out, int B, int L, int D,
-                                int mix_cutoff, float psi, int trunc_cutoff) {
+                                int mix_cutoff, float psi, int trunc_cutoff, const int* __restrict__ cutoff_dev = nullptr) {
+  if (cutoff_dev) mix_cutoff = *cutoff_dev;
   const long long total = (long long)B * L * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -719,7 +721,9 @@ __global__ void dlatents_kernel(const float* __restrict__ w1, const float* __res
 }
 
 __global__ void dlatents_bwd_kernel(const float* __restrict__ g, float* __restrict__ gw1, float* __restrict__ gw2,
-                                    int B, int L, int D, int mix_cutoff, float psi, int trunc_cutoff, int has_trunc) {
+                                    int B, int L, int D, int mix_cutoff, float psi, int trunc_cutoff, int has_trunc,
+                                    const int* __restrict__ cutoff_dev = nullptr) {
+  if (cutoff_dev) mix_cutoff = *cutoff_dev;
   const long long total = (long long)B * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -872,6 +876,16 @@ SG_EXPORT int sg_axpby(const void* x, const void* y, void* out, float a, float b
     axpby_kernel<T><<<sg_grid_1d(n / SgVec<T>::N + 1, 256, 148 * 32), 256, 0, st>>>((const T*)x, (const T*)y, (T*)out, a, b, n);
   });
   return sg_check_launch("sg_axpby");
+}
+
+SG_EXPORT int sg_axpby_dev(const void* x, const void* y, void* out, const float* ab, long long n, int dtype,
+                           void* stream) {
+  SG_REQUIRE(ab != nullptr, "sg_axpby_dev: coefficient pointer missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_DISPATCH(dtype, {
+    axpby_kernel<T><<<sg_grid_1d(n / SgVec<T>::N + 1, 256, 148 * 32), 256, 0, st>>>((const T*)x, (const T*)y, (T*)out, 0.f, 0.f, n, ab);
+  });
+  return sg_check_launch("sg_axpby_dev");
 }
 
 SG_EXPORT int sg_lrelu_bwd(const void* g, const void* ref, void* gx, long long n, int dtype, void* stream) {
@@ -1047,6 +1061,22 @@ SG_EXPORT int sg_dlatents_bwd(const float* g, float* gw1, float* gw2, int B, int
   long long total = (long long)B * D;
   dlatents_bwd_kernel<<<sg_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(g, gw1, gw2, B, L, D, mix_cutoff, psi, trunc_cutoff, has_trunc);
   return sg_check_launch("sg_dlatents_bwd");
+}
+
+// the style-mixing cut-off read from device memory (one int), for CUDA-graph replay
+SG_EXPORT int sg_dlatents_dev(const float* w1, const float* w2, const float* avg, float* out, int B, int L, int D,
+                              const int* mix_cutoff, float psi, int trunc_cutoff, void* stream) {
+  SG_REQUIRE(mix_cutoff != nullptr, "sg_dlatents_dev: cut-off pointer missing");
+  long long total = (long long)B * L * D;
+  dlatents_kernel<<<sg_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(w1, w2, avg, out, B, L, D, 0, psi, trunc_cutoff, mix_cutoff);
+  return sg_check_launch("sg_dlatents_dev");
+}
+SG_EXPORT int sg_dlatents_bwd_dev(const float* g, float* gw1, float* gw2, int B, int L, int D, const int* mix_cutoff,
+                                  float psi, int trunc_cutoff, int has_trunc, void* stream) {
+  SG_REQUIRE(mix_cutoff != nullptr, "sg_dlatents_bwd_dev: cut-off pointer missing");
+  long long total = (long long)B * D;
+  dlatents_bwd_kernel<<<sg_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(g, gw1, gw2, B, L, D, 0, psi, trunc_cutoff, has_trunc, mix_cutoff);
+  return sg_check_launch("sg_dlatents_bwd_dev");
 }
 
 SG_EXPORT int sg_up2_nhwc(const void* x, void* y, float scale, int dtype, int N, int H, int W, int C, void* stream) {

@@ -153,6 +153,13 @@ class GSynthesis(nn.Module):
             x_hi = self.blocks[depth - 1].forward_nhwc(x, dl[:, 2 * depth:2 * (depth + 1)])
             # straight and residual branches + fade-in in one fused to_rgb (reference GAN.py:199-202); the nearest
             # up-sampling of the residual branch happens inside the kernel
+            if isinstance(alpha, _ops.DynScalar):
+                # alpha lives in device memory (CUDA-graph replay): evaluate both branches with unit weights -- the
+                # residual one at the low resolution, the 1x1 convolution commutes with nearest up-sampling -- and
+                # blend with the coefficient pair read by the kernel at run time
+                hi = self._rgb(x_hi, depth, 1.0)
+                lo = _ops.UpsampleNCHW.apply(self._rgb(x, depth - 1, 1.0), 2, 1.0)
+                return _ops.Axpby.apply(hi, lo, alpha, None)
             return self._rgb(x_hi, depth, float(alpha), x, depth - 1, 1.0 - float(alpha))
         raise KeyError("Unknown structure: ", self.structure)
 
@@ -162,6 +169,15 @@ def _upsample_feature(x_nhwc):
     planes = _ops.Cast.apply(x_nhwc, torch.float32).permute(0, 3, 1, 2).contiguous()
     up = _ops.UpsampleNCHW.apply(planes, 2, 1.0)
     return _ops.Cast.apply(up.permute(0, 2, 3, 1).contiguous(), x_nhwc.dtype)
+
+
+def draw_style_mixing(shape, depth, prob):
+    """The host RNG draws of one training-mode Generator.forward, in the reference's order (GAN.py:282, 287-288):
+    torch.randn on the CPU generator, then random.random() / random.randint().  -> (latents2 on the host, cut-off)"""
+    latents2 = torch.randn(shape)
+    cur_layers = 2 * (depth + 1)
+    cutoff = random.randint(1, cur_layers) if random.random() < prob else cur_layers
+    return latents2, cutoff
 
 
 class Generator(nn.Module):
@@ -215,11 +231,16 @@ class Generator(nn.Module):
         if self.style_mixing_prob is not None and self.style_mixing_prob > 0:
             # host RNG consumption order identical to the reference: torch.randn on the CPU generator, then
             # random.random() / random.randint()
-            latents2 = torch.randn(latents_in.shape).to(latents_in.device)
+            cap = _ops.capture_ctx()
+            if cap is not None:
+                # CUDA-graph capture: the host draws are made by the replay driver (same calls, same order) and arrive
+                # through device buffers
+                latents2, cutoff = cap.next_mixing(latents_in.shape)
+            else:
+                latents2, cutoff = draw_style_mixing(latents_in.shape, depth, self.style_mixing_prob)
+                latents2 = latents2.to(latents_in.device)
             w2 = self.g_mapping(latents2)
             w2 = w2[:, 0] if w2.dim() == 3 else w2
-            cur_layers = 2 * (depth + 1)
-            cutoff = random.randint(1, cur_layers) if random.random() < self.style_mixing_prob else cur_layers
         if self.truncation is not None:
             dlatents = _ops.Dlatents.apply(w1, w2, self.truncation.avg_latent, L, cutoff, self.truncation.threshold,
                                            self.truncation.max_layer)
@@ -303,7 +324,7 @@ class Discriminator(nn.Module):
                 residual = self._from_rgb(self.temporaryDownsampler(images_in), self.depth - depth)
                 straight = self.blocks[self.depth - depth - 1].forward_nhwc(
                     self._from_rgb(images_in, self.depth - depth - 1))
-                x = _ops.Axpby.apply(straight, residual, float(alpha), 1.0 - float(alpha))
+                x = _ops.Axpby.apply(straight, residual, *_ops.lerp_coefs(alpha))
                 for block in self.blocks[(self.depth - depth):]:
                     x = block.forward_nhwc(x)
             else:
@@ -332,6 +353,7 @@ class StyleGAN:
             raise RuntimeError("sgb200: StyleGAN runs on a CUDA device only (got %s); the reference's CPU path has "
                                "no counterpart here" % (self.device,))
         self.d_repeats = d_repeats
+        self.use_cuda_graphs = os.environ.get("SG_CUDA_GRAPHS", "1") != "0"
         self.conditional = conditional
         self.n_classes = n_classes
         self.use_ema = use_ema
@@ -352,6 +374,8 @@ class StyleGAN:
         self.__setup_dis_optim(**d_opt_args)
         self.drift = drift
         self.loss = self.__setup_loss(loss)
+        from . import _graphs
+        self._graphs = _graphs.StepGraphs(self)
 
         if self.use_ema:
             self.gen_shadow = copy.deepcopy(self.gen)
@@ -395,13 +419,20 @@ class StyleGAN:
             prior = _ops.UpsampleNCHW.apply(_ops.PoolNCHW.apply(real_batch, pf, 1.0 / (pf * pf)), 2, 1.0)
         else:
             prior = ds
-        return _ops.Axpby.apply(ds.contiguous(), prior.contiguous(), float(alpha), 1.0 - float(alpha))
+        return _ops.Axpby.apply(ds.contiguous(), prior.contiguous(), *_ops.lerp_coefs(alpha))
 
     def optimize_discriminator(self, noise, real_batch, depth, alpha, labels=None):
-        """One discriminator update (reference GAN.py:591-622).  Returns the loss value (host float)."""
+        """One discriminator update (reference GAN.py:591-622).  Returns the loss value (host float).
+        After two eager calls per (depth, batch shape) the update is replayed from a captured CUDA graph
+        (models/_graphs.py; `self.use_cuda_graphs = False` or SG_CUDA_GRAPHS=0 keeps it eager)."""
+        loss = self._graphs.run("D", self._d_step, noise, real_batch, depth, alpha, labels)
+        return loss.item() / self.d_repeats
+
+    def _d_step(self, noise, real_batch, depth, alpha, labels=None):
+        """Device-side part of optimize_discriminator: -> sum of the d_repeats loss values (0-d device tensor)."""
         with torch.no_grad():
             real_samples = self.__progressive_down_sampling(real_batch, depth, alpha)
-        loss_val = 0
+        loss_sum = None
         for _ in range(self.d_repeats):
             with torch.no_grad():                              # the reference builds, then detaches, this graph
                 fake_samples = self.gen(noise, depth, alpha, labels).detach()
@@ -413,11 +444,15 @@ class StyleGAN:
             loss.backward()
             gscale = self.ddp.allreduce_grads(self.dis_optim) if self.ddp is not None else 1.0
             self.dis_optim.step(grad_scale=gscale)
-            loss_val += loss.item()
-        return loss_val / self.d_repeats
+            loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
+        return loss_sum
 
     def optimize_generator(self, noise, real_batch, depth, alpha, labels=None):
         """One generator update incl. gradient clipping and EMA (reference GAN.py:624-659)."""
+        return self._graphs.run("G", self._g_step, noise, real_batch, depth, alpha, labels).item()
+
+    def _g_step(self, noise, real_batch, depth, alpha, labels=None):
+        """Device-side part of optimize_generator: -> loss (0-d device tensor)."""
         real_samples = None
         # the built-in losses below ignore the reals in gen_loss (reference Losses.py:84,128,151,227), so the pyramid
         # the reference always computes (GAN.py:636) is skipped for them only; any other loss object receives it
@@ -451,7 +486,7 @@ class StyleGAN:
         if shadow is not None:
             ema_map = {p: shadow[n] for n, p in self.gen.named_parameters()}
         self.gen_optim.step(max_norm=10., ema_map=ema_map, ema_decay=self.ema_decay, grad_scale=gscale)
-        return loss.item()
+        return loss.detach()
 
     @staticmethod
     def create_grid(samples, scale_factor, img_file):

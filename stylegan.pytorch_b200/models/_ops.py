@@ -17,7 +17,7 @@ from . import _geom
 from ._lib import lib, ptr, stream, code, count_launch
 
 _state = {"dtype": torch.float32, "use_tc": True, "skip_param_grads": False, "fused_updown": True, "use_pair": True,
-          "fuse_epilogue": True}
+          "fuse_epilogue": True, "wgrad_v2": True}
 
 
 class skip_param_grads:
@@ -49,6 +49,58 @@ def precision():
 
 def set_use_tc(flag):
     _state["use_tc"] = bool(flag)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-step values that must not be baked into a captured CUDA graph (models/_graphs.py)
+# ---------------------------------------------------------------------------------------------------------------
+class DynScalar:
+    """A per-step float pair (v, w) in device memory -- e.g. the fade-in (alpha, 1 - alpha).  Axpby(x, y, d, None)
+    computes v*x + w*y with both read by the kernel at run time; `float(d)` is the host value of v."""
+
+    def __init__(self, dev, value):
+        self.dev, self.value = dev, float(value)           # dev: float32 tensor with >= 1 element
+
+    def __float__(self):
+        return self.value
+
+    @property
+    def second(self):
+        """the DynScalar whose first element is this one's w"""
+        return DynScalar(self.dev[1:], float("nan"))
+
+
+class DynInt:
+    """A per-step int in device memory (the style-mixing cut-off)."""
+
+    def __init__(self, dev, value):
+        self.dev, self.value = dev, int(value)             # dev: int32 tensor [1]
+
+    def __int__(self):
+        return self.value
+
+
+_capture = [None]          # the active models/_graphs.py capture context, if any
+
+
+def capture_ctx():
+    return _capture[0]
+
+
+def upload_table(t, device):
+    """Small CPU tensor -> device.  During a CUDA-graph capture the copy must come from pinned memory that outlives the
+    graph (the copy node re-reads the host address at every replay): the capture context owns such an arena."""
+    c = _capture[0]
+    if c is not None:
+        return c.pinned_copy(t).to(device, non_blocking=True)
+    return t.to(device, non_blocking=True)
+
+
+def lerp_coefs(alpha):
+    """(a, b) for a*x + b*y = lerp(y, x, alpha): python floats, or (DynScalar, None) when alpha lives on the device."""
+    if isinstance(alpha, DynScalar):
+        return alpha, None
+    return float(alpha), 1.0 - float(alpha)
 
 
 def _require_cuda(t):
@@ -322,7 +374,11 @@ class Axpby(Function):
             y = _c(y)
             assert y.shape == x.shape and y.dtype == x.dtype
         out = torch.empty_like(x)
-        lib.sg_axpby(ptr(x), ptr(y), ptr(out), float(a), float(b), x.numel(), code(x.dtype), stream())
+        if isinstance(a, DynScalar):
+            lib.sg_axpby_dev(ptr(x), ptr(y), ptr(out), ptr(a.dev), x.numel(), code(x.dtype), stream())
+            b = a.second
+        else:
+            lib.sg_axpby(ptr(x), ptr(y), ptr(out), float(a), float(b), x.numel(), code(x.dtype), stream())
         count_launch()
         ctx.cfg = (a, b, y is not None)
         return out
@@ -555,8 +611,7 @@ def _pack_scales(scale, bias_mul):
 
 def _lingroup_table(rows, device):
     """rows: list of 8 python ints per group -> int64 device tensor (one small host-to-device copy)."""
-    t = torch.tensor(rows, dtype=torch.int64).reshape(-1, 8)
-    return t.to(device, non_blocking=True)
+    return upload_table(torch.tensor(rows, dtype=torch.int64).reshape(-1, 8), device)
 
 
 class StyleAffines(Function):
@@ -1019,8 +1074,12 @@ class Dlatents(Function):
         w1 = _c(w1)
         B, D = w1.shape
         out = torch.empty((B, L, D), dtype=torch.float32, device=w1.device)
-        lib.sg_dlatents(ptr(w1), ptr(_c(w2) if w2 is not None else None), ptr(avg), ptr(out), B, L, D,
-                        int(mix_cutoff), float(psi), int(trunc_cutoff), stream())
+        if isinstance(mix_cutoff, DynInt):
+            lib.sg_dlatents_dev(ptr(w1), ptr(_c(w2) if w2 is not None else None), ptr(avg), ptr(out), B, L, D,
+                                ptr(mix_cutoff.dev), float(psi), int(trunc_cutoff), stream())
+        else:
+            lib.sg_dlatents(ptr(w1), ptr(_c(w2) if w2 is not None else None), ptr(avg), ptr(out), B, L, D,
+                            int(mix_cutoff), float(psi), int(trunc_cutoff), stream())
         count_launch()
         ctx.cfg = (L, mix_cutoff, psi, trunc_cutoff, w2 is not None, avg is not None)
         return out
@@ -1033,8 +1092,12 @@ class Dlatents(Function):
         B, _, D = g.shape
         g1 = torch.empty((B, D), dtype=torch.float32, device=g.device)
         g2 = torch.empty((B, D), dtype=torch.float32, device=g.device) if has2 else None
-        lib.sg_dlatents_bwd(ptr(g), ptr(g1), ptr(g2), B, L, D, int(mix_cutoff), float(psi), int(trunc_cutoff),
-                            int(has_trunc), stream())
+        if isinstance(mix_cutoff, DynInt):
+            lib.sg_dlatents_bwd_dev(ptr(g), ptr(g1), ptr(g2), B, L, D, ptr(mix_cutoff.dev), float(psi),
+                                    int(trunc_cutoff), int(has_trunc), stream())
+        else:
+            lib.sg_dlatents_bwd(ptr(g), ptr(g1), ptr(g2), B, L, D, int(mix_cutoff), float(psi), int(trunc_cutoff),
+                                int(has_trunc), stream())
         count_launch()
         return g1, g2, None, None, None, None, None
 
@@ -1042,7 +1105,13 @@ class Dlatents(Function):
 def randn_device(shape, device, seed, offset):
     """N(0,1) fp32 noise from the engine's Philox generator (NoiseLayer, CustomLayers.py:193)."""
     out = torch.empty(shape, dtype=torch.float32, device=device)
-    lib.sg_randn(ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), int(offset), stream())
+    c = _capture[0]
+    if c is not None:
+        # inside a CUDA-graph capture: counter = (device) base of this step + the offset inside the step
+        lib.sg_randn_dev(ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), ptr(c.rng_base), int(offset) - c.rng_offset0,
+                         stream())
+    else:
+        lib.sg_randn(ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), int(offset), stream())
     count_launch()
     return out
 

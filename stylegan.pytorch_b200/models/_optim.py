@@ -18,7 +18,7 @@ def _table(entries, device):
         rows.append([p_ptr, g_ptr, m_ptr, v_ptr, e_ptr, s_ptr, n, c0])
         c0 += (n + chunk - 1) // chunk
     t = torch.tensor(rows, dtype=torch.int64).reshape(-1, 8)
-    return t.to(device), c0
+    return _ops.upload_table(t, device), c0
 
 
 def ema_update(pairs, beta):

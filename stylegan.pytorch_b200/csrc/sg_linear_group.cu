@@ -57,9 +57,11 @@ __global__ void __launch_bounds__(256) lingroup_fwd_kernel(const LinGroup* __res
     for (int v = 0; v < IV; ++v) w[r][v] = *reinterpret_cast<const float4*>(Wp + (size_t)o * I + v * 128 + lane * 4);
   }
   const float* xp = reinterpret_cast<const float*>(t.x);
-  for (int i = threadIdx.x; i < B * (I / 4); i += blockDim.x) {
+  const int B8 = (B + 7) & ~7;                         // rows are consumed eight at a time: pad with zeros
+  for (int i = threadIdx.x; i < B8 * (I / 4); i += blockDim.x) {
     const int b = i / (I / 4), c = i % (I / 4);
-    reinterpret_cast<float4*>(xs)[i] = *reinterpret_cast<const float4*>(xp + (size_t)b * t.ldx + c * 4);
+    reinterpret_cast<float4*>(xs)[i] = b < B ? *reinterpret_cast<const float4*>(xp + (size_t)b * t.ldx + c * 4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   const float scale = lo_f(t.scales), bmul = hi_f(t.scales);
@@ -203,7 +205,7 @@ SG_EXPORT int sg_lingroup_fwd(const void* table, int G, int total_blocks, int B,
   SG_REQUIRE(sg_lingroup_supported(B, I), "sg_lingroup_fwd: B must be <= 32 and I in {128, 256, 512}");
   const LinGroup* tab = reinterpret_cast<const LinGroup*>(table);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)B * I * sizeof(float);
+  const size_t smem = (size_t)((B + 7) & ~7) * I * sizeof(float);
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(lingroup_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);

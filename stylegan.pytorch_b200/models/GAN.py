@@ -3,9 +3,10 @@
 ``StyleGAN`` -- same constructor signatures, attribute names, state_dict keys, parameter registration order and
 checkpoint files, so the reference's train.py / generate_*.py run against this package unchanged.
 
-The per-step hot path (optimize_discriminator / optimize_generator) runs on the sgb200 CUDA kernels; under
-torch.distributed (one process per GPU, NCCL) gradients are all-reduced in flat buckets on a side stream
-(models/_ddp.py) before the fused Adam step."""
+The per-step hot path (optimize_discriminator / optimize_generator) runs on the sgb200 CUDA kernels and, after two
+eager calls, as a replayed CUDA graph (models/_graphs.py); under torch.distributed (one process per GPU, NCCL) the
+gradients of each optimizer are all-reduced in one flat bucket after its backward (models/_ddp.py) and consumed in
+place by the fused Adam step."""
 import copy
 import datetime
 import os

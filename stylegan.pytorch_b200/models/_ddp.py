@@ -1,9 +1,16 @@
-"""Data-parallel gradient exchange: one process per GPU, flat fp32 gradient buckets all-reduced over NCCL
-(NVLink 5 / NVSwitch) on a side stream, overlapped with the fused optimizer work of earlier buckets.
+"""Data-parallel gradient exchange: one process per GPU; after each backward the gradients of one optimizer are packed
+into flat fp32 buckets (one bucket per optimizer at the default size: ~92 MB for D, ~100 MB for G at 256x256) and
+SUM-all-reduced over NCCL (NVLink 5 / NVSwitch); every `.grad` is then re-pointed into its bucket, so the multi-tensor
+Adam kernel consumes the reduced values in place with the 1/world average folded into its gradient scale (and into the
+clip norm).  The exchange is NOT overlapped with the backward pass: it starts when the backward has finished and the
+optimizer waits for it (at 8 GPUs ~0.3 ms of NVLink time per optimizer against a ~20 ms step half; what the scaling
+runs lose is mostly the max-over-ranks of the per-step time, which the CUDA-graph replay of the step removes).
+Inside a captured step (models/_graphs.py) the all-reduce is a node of the graph.
 
 The reference has no multi-GPU code at all (`# TODO` at models/GAN.py:509-510); semantics follow SURVEY.md 8(e):
-identical replicas, per-rank local batch, gradients averaged (sum then 1/world folded into the Adam kernel), rank-0
-broadcast of parameters and buffers at start.  Works with the gloo backend on CPU tensors for the host-logic tests."""
+identical replicas, per-rank local batch, gradients averaged, rank-0 broadcast of parameters and buffers at start,
+Truncation.avg_latent averaged over the ranks after each update.  Works with the gloo backend on CPU tensors for the
+host-logic tests."""
 import os
 
 import torch
@@ -25,12 +32,11 @@ def bucketize(sizes, bucket_elems):
 
 
 class DataParallelContext:
-    def __init__(self, device, bucket_elems=8 * 1024 * 1024):
+    def __init__(self, device, bucket_elems=64 * 1024 * 1024):
         self.device = device
         self.rank = dist.get_rank()
         self.world = dist.get_world_size()
-        self.bucket_elems = bucket_elems
-        self.comm_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
+        self.bucket_elems = bucket_elems        # one NCCL call per optimizer: large messages ride NVLS / the ring at full rate
 
     @classmethod
     def from_env(cls, device):
@@ -52,9 +58,8 @@ class DataParallelContext:
         return t
 
     def reduce_buckets(self, grads):
-        """grads: list of tensors (same device).  Returns (flats, placement) where flats are SUM-reduced flat
-        buckets and placement[i] = (bucket_index, offset).  All-reduces are issued asynchronously; the caller must
-        call `wait()` on each returned work handle (done in allreduce_grads)."""
+        """grads: list of tensors (same device).  Returns (flats, works, placement): flats are the flat buckets being
+        SUM-reduced (asynchronously; wait on `works`), placement[i] = (bucket_index, offset)."""
         sizes = [g.numel() for g in grads]
         plan = bucketize(sizes, self.bucket_elems)
         flats, works, placement = [], [], [None] * len(grads)

@@ -52,11 +52,11 @@ class FusedAdam(torch.optim.Adam):
         return st
 
     @torch.no_grad()
-    def step(self, closure=None, max_norm=None, ema_map=None, ema_decay=0.999, grad_scale=1.0, flat_grads=None):
+    def step(self, closure=None, max_norm=None, ema_map=None, ema_decay=0.999, grad_scale=1.0):
         """max_norm: clip_grad_norm_ threshold applied to the (scaled) gradients of THIS optimizer's parameters.
         ema_map: {param: shadow_param}; updated in the same pass (parameters without a gradient are averaged in a
         second launch, as models/__init__.py:update_average touches every parameter).
-        flat_grads: {param: (flat_tensor, offset)} when gradients live in all-reduced flat buckets."""
+        grad_scale: multiplies every gradient (1/world after a SUM all-reduce, models/_ddp.py)."""
         assert closure is None
         for group in self.param_groups:
             lr, (b1, b2), eps = group["lr"], group["betas"], group["eps"]
@@ -71,14 +71,10 @@ class FusedAdam(torch.optim.Adam):
                 _ops._require_cuda(p)
                 dev = p.device
                 st = self._state_for(p)
-                if flat_grads is not None and p in flat_grads:
-                    flat, off = flat_grads[p]
-                    g_ptr = flat.data_ptr() + 4 * off
-                else:
-                    if not g.is_contiguous() or g.dtype != torch.float32:
-                        g = g.contiguous().float()
-                        p.grad = g
-                    g_ptr = g.data_ptr()
+                if not g.is_contiguous() or g.dtype != torch.float32:
+                    g = g.contiguous().float()
+                    p.grad = g
+                g_ptr = g.data_ptr()
                 e_ptr = ema_map[p].data_ptr() if (ema_map is not None and p in ema_map) else 0
                 entries.append((p.data_ptr(), g_ptr, st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), e_ptr,
                                 st["step"].data_ptr(), p.numel()))

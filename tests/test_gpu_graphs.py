@@ -64,10 +64,13 @@ def test_graph_replay_equals_eager(precision, loss):
     assert cap_e == 0 and cap_g == 2                      # one graph per step kind
     # fp32: the two paths run the same kernels on the same data; what differs is the atomics' summation order
     # (fp64 InstanceNorm partials on the unfused layers) -> round-off level.  bf16: LeakyReLU mask flips amplify it.
-    tol = 2e-4 if precision == "fp32" else 3e-2
-    for (de, ge), (dg, gg) in zip(eager, graph):
-        assert abs(de - dg) <= tol * max(1.0, abs(de)), (eager, graph)
-        assert abs(ge - gg) <= tol * max(1.0, abs(ge)), (eager, graph)
+    # The first two steps run the same eager code in both runs; from the third on one of them is a replay.  A GAN step
+    # is a chaotic map (Adam with beta1 = 0 turns round-off-sized gradient differences into +-lr parameter steps), so the
+    # bound opens up with the step index.
+    for i, ((de, ge), (dg, gg)) in enumerate(zip(eager, graph)):
+        tol = (1e-5 if i < 2 else 3e-3) if precision == "fp32" else (1e-5 if i < 2 else 5e-2)
+        assert abs(de - dg) <= tol * max(1.0, abs(de)), (i, eager, graph)
+        assert abs(ge - gg) <= tol * max(1.0, abs(ge)), (i, eager, graph)
     worst = max(rel(st_g[k], st_e[k]) for k in st_e if st_e[k].dtype.is_floating_point and st_e[k].numel() > 1)
     assert worst < (5e-3 if precision == "fp32" else 1e-1), worst
 

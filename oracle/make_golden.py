@@ -271,6 +271,65 @@ def golden_full_width(name, res, batch, seed, alpha=0.5):
           (fx["d_loss"], fx["g_loss"], fx["r1"]))
 
 
+def golden_standard_and_conditional(name, arch, batch, depth, alpha, n_classes=4, seed=5):
+    """The two remaining loss classes of the reference evaluated by the reference itself (models/Losses.py:54-133):
+    StandardGAN.dis_loss on the unconditional discriminator (its gen_loss unpacks a 3-tuple the discriminator never
+    returns, Losses.py:131, and cannot be executed), and ConditionalGANLoss.dis_loss / gen_loss on the CONDITIONAL
+    generator + discriminator (class embeddings, GAN.py:233-236, 326-369, 395-437), with per-parameter gradient norms."""
+    from models.Losses import StandardGAN, ConditionalGANLoss
+    from models.GAN import Generator, Discriminator
+    seed_all(seed)
+    sg = build_reference(arch)
+    randomize_zero_inits(sg)
+    sg.dis.train()
+    res = 2 ** (depth + 2)
+    real = torch.randn(batch, arch.num_channels, res, res)
+    fake_in = torch.randn(batch, arch.num_channels, res, res)
+    dn = [n for n, _ in sg.dis.named_parameters()]
+    L = StandardGAN(sg.dis)
+    dl = L.dis_loss(real, fake_in, depth, alpha)
+    dg = torch.autograd.grad(dl, list(sg.dis.parameters()), allow_unused=True)
+    fx = dict(arch=arch.__dict__.copy(), batch=batch, depth=depth, alpha=alpha, n_classes=n_classes,
+              d_init=clone_sd(sg.dis.state_dict()), real=real, fake_in=fake_in,
+              standard=dict(d_loss=float(dl.detach()),
+                            d_grad_norms={n: float(g.norm()) for n, g in zip(dn, dg) if g is not None}))
+    # conditional networks
+    gk, dk = arch.g_kwargs(), arch.d_kwargs()
+    gen = Generator(conditional=True, n_classes=n_classes, **gk)
+    dis = Discriminator(conditional=True, n_classes=n_classes, **dk)
+    with torch.no_grad():
+        for net in (gen, dis):
+            for n, p in net.named_parameters():
+                if n.endswith("noise.weight"):
+                    p.copy_(torch.randn_like(p))
+                elif n.endswith(".bias") and "init_block.bias" not in n:
+                    p.copy_(0.1 * torch.randn_like(p))
+    gen.train(); dis.train()
+    noises = set_noise(gen, batch)
+    z = torch.randn(batch, arch.latent_size)
+    labels = torch.randint(0, n_classes, (batch,))
+    mix = record_mixing(arch, (batch, 2 * arch.latent_size), depth)       # the conditional latent is [z | embedding]
+    g_init, dc_init = clone_sd(gen.state_dict()), clone_sd(dis.state_dict())
+    fake = gen(z, depth, alpha, labels)
+    CL = ConditionalGANLoss(dis)
+    logits_real = dis(real, depth, alpha, labels_in=labels)
+    cdl = CL.dis_loss(real, fake.detach(), labels, depth, alpha)
+    cdg = torch.autograd.grad(cdl, list(dis.parameters()), allow_unused=True)
+    cgl = CL.gen_loss(None, fake, labels, depth, alpha)
+    cgg = torch.autograd.grad(cgl, list(gen.parameters()), allow_unused=True)
+    fx["conditional"] = dict(g_init=g_init, d_init=dc_init, noises=noises[:2 * (depth + 1)], z=z, labels=labels, mix=mix,
+                             fake=fake.detach().clone(), logits_real=logits_real.detach().clone(),
+                             d_loss=float(cdl.detach()), g_loss=float(cgl.detach()),
+                             d_grad_norms={n: float(g.norm()) for (n, _), g in zip(dis.named_parameters(), cdg)
+                                           if g is not None},
+                             g_grad_norms={n: float(g.norm()) for (n, _), g in zip(gen.named_parameters(), cgg)
+                                           if g is not None})
+    out = os.path.join(ROOT, "tests", "golden", name + ".pt")
+    torch.save(fx, out)
+    print(name, "->", out, "%.1f KB" % (os.path.getsize(out) / 1024), "standard d_loss %.5f; conditional d/g %.5f %.5f"
+          % (fx["standard"]["d_loss"], fx["conditional"]["d_loss"], fx["conditional"]["g_loss"]))
+
+
 def live_full_width(outdir):
     """BASELINE config 1 at the reference's real channel widths (too large to commit): resolution-128 config,
     depth 1 (8x8) and depth 2 (16x16), batch 4.  Used by tests/test_oracle_vs_reference.py in the build container."""
@@ -280,6 +339,11 @@ def live_full_width(outdir):
 
 
 def main():
+    if len(sys.argv) >= 2 and sys.argv[1] == "--losses":
+        tiny16 = O.Arch(16, latent_size=32, dlatent_size=512, mapping_fmaps=32, mapping_layers=4, fmap_base=128,
+                        fmap_max=32)
+        golden_standard_and_conditional("losses2_tiny16_d2", tiny16, batch=4, depth=2, alpha=0.5)
+        return
     if len(sys.argv) >= 2 and sys.argv[1] == "--full":
         # BASELINE configs 2 and 3 at full width (minutes of CPU): python oracle/make_golden.py --full
         golden_full_width("full128_d5", 128, batch=4, seed=11)

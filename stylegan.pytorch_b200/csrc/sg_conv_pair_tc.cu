@@ -32,7 +32,6 @@ constexpr int HALO_ROWS = (TH + 2) * TW;           // 160 smem rows of 128 B per
 constexpr int A_BYTES = HALO_ROWS * BK * 2;        // 20480
 constexpr int NUM_THREADS = 192;
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 struct __align__(8) Barriers {
   uint64_t full[MAX_STAGES];      // leader's copy is used: expect_tx by the leader, complete_tx from both CTAs' TMA
@@ -59,112 +58,8 @@ struct Params {
   __nv_bfloat16* y;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-      " selp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
-  }
-}
-// TMA loads of a CTA pair: the bytes land in the executing CTA's shared memory, the completion goes to the mbarrier at
-// the same offset in the LEADER CTA (rank bit cleared), which the MMA-issuing warp waits on.
-__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                             int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-      "%5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1),
-        "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-      "[%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n .reg .b64 da, db;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n"
-      " setp.ne.b32 p, %6, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}\n"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives (once the MMAs issued so far have completed) on the mbarrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)0x3)
-               : "memory");
-}
-
-// 64 per-lane values (one per channel of this lane's pixel) -> per-warp column sums, two channels per lane:
-// lane l ends up with the sums of channels 2l and 2l+1 in out0/out1.  31 exchange rounds halve the live set each time.
-__device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane, float& out0, float& out1) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {             // keep channels whose bit 5 == lane bit 4
-    const bool up = lane & 16;
-    const float keep = up ? v[i + 32] : v[i], send = up ? v[i] : v[i + 32];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool up = lane & 8;
-    const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 4;
-    const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 2;
-    const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 1;
-    const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  out0 = v[0];
-  out1 = v[1];
-}
-// channel held by (lane, j) after warp_colsum64: bit5 = lane bit4, bit4 = lane bit3, ..., bit1 = lane bit0, bit0 = j
-__device__ __forceinline__ int colsum_channel(int lane, int j) {
-  return ((lane & 16) << 1) | ((lane & 8) << 1) | ((lane & 4) << 1) | ((lane & 2) << 1) | ((lane & 1) << 1) | j;
-}
+// statistics layout: after the per-warp column sums lane l holds channels 2l and 2l+1 of the 64-channel chunk
+__device__ __forceinline__ int colsum_channel(int lane, int j) { return 2 * lane + j; }
 
 template <bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -185,6 +80,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   __shared__ float s_bias[256], s_nw[256];
   __shared__ float s_red[4][2][64];                      // cross-warp combine of the statistics (one 64-ch chunk)
+  // per-warp staging of one 32-pixel x 64-channel bf16 block (4 KB, 16-byte chunks XOR-swizzled by the pixel row so that
+  // both the row-wise 16-byte stores and the column-wise 4-byte loads are bank-conflict free).  Column sums through
+  // shared memory cost ~64 wavefronts per warp and chunk; a shuffle butterfly (tried first: 248 SHFL per warp and
+  // chunk) made the epilogue 3x slower than the MMAs it has to hide behind.
+  __shared__ __align__(16) uint8_t s_stage[STATS ? 4 * 4096 : 16];
   for (int i = threadIdx.x; i < p.BN; i += blockDim.x) {
     s_bias[i] = p.bias ? p.bias[n0 + i] * p.bias_mul : 0.f;
     s_nw[i] = (p.noise && p.noise_w) ? p.noise_w[n0 + i] : 0.f;
@@ -355,7 +255,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tmem_ld16_nowait(taddr + c0 + 32, v2);
         tmem_ld16_nowait(taddr + c0 + 48, v3);
         tmem_ld_wait();
-        float zf[64];
+        uint8_t* srow = s_stage + (STATS ? qd * 4096 + lane * 128 : 0);
         auto emit16 = [&](const uint32_t (&v)[16], int o) {
           uint32_t packed[8];
 #pragma unroll
@@ -368,26 +268,33 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             if (p.act) { a = fmaxf(a, SG_LRELU_SLOPE * a); b = fmaxf(b, SG_LRELU_SLOPE * b); }
             __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-            const uint32_t w = *reinterpret_cast<uint32_t*>(&h2);
-            packed[jj] = w;
-            if (STATS) {                                    // statistics of the ROUNDED values (what the consumer reads)
-              zf[o + 2 * jj] = __uint_as_float(w << 16);
-              zf[o + 2 * jj + 1] = __uint_as_float(w & 0xffff0000u);
-            }
+            packed[jj] = *reinterpret_cast<uint32_t*>(&h2);
           }
           st_global_256(dst + c0 + o, packed);
+          if (STATS) {                                      // the ROUNDED values, as the consumer will read them
+            const int ch = o >> 3;                          // logical 16-byte chunk of this pixel row (8 channels each)
+            *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ (lane & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ (lane & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          }
         };
         emit16(v0, 0);
         emit16(v1, 16);
         emit16(v2, 32);
         emit16(v3, 48);
         if (STATS) {
-          float sq[64];
+          __syncwarp();
+          // lane l sums channels 2l, 2l+1 (one 32-bit word) over the warp's 32 pixel rows
+          const uint8_t* sblk = s_stage + qd * 4096 + ((lane & 3) << 2);
+          const int lch = lane >> 2;
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 64; ++i) sq[i] = zf[i] * zf[i];
-          float a0, a1, b0, b1;
-          warp_colsum64(zf, lane, a0, a1);
-          warp_colsum64(sq, lane, b0, b1);
+          for (int r = 0; r < 32; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sblk + r * 128 + ((lch ^ (r & 7)) << 4));
+            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+            a0 += lo; a1 += hi;
+            b0 = fmaf(lo, lo, b0); b1 = fmaf(hi, hi, b1);
+          }
+          __syncwarp();                                     // the next chunk overwrites the staging block
           st_s[c][0] += a0; st_s[c][1] += a1;
           st_q[c][0] += b0; st_q[c][1] += b1;
         }
@@ -463,7 +370,7 @@ struct Plan {
   size_t smem;
 };
 
-static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl) {
+static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl, bool stats = true) {
   if (N < 1 || H % TH != 0 || W % TW != 0 || Cin % BK != 0 || Cin < BK) return false;
   const int BN = pick_bn(Cout);
   if (!BN) return false;
@@ -476,7 +383,9 @@ static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl) {
   pl->resident = resident_ok(Cin, pl->HB) ? 1 : 0;
   pl->w_bytes = pl->resident ? 9 * pl->kchunks * pl->HB * BK * 2 : 0;
   pl->stage_bytes = pl->resident ? A_BYTES : A_BYTES + 3 * pl->HB * BK * 2;
-  int stages = (214 * 1024 - pl->w_bytes) / pl->stage_bytes;
+  // 227 KB per CTA = static (bias / noise weights / reduction scratch 4 KB, + 16 KB statistics staging) + dynamic
+  const int budget = 232448 - (stats ? 20608 : 4224) - (int)sizeof(Barriers) - 1024 - 256;
+  int stages = (budget - pl->w_bytes) / pl->stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return false;
   pl->stages = stages;
@@ -500,7 +409,8 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(conv3x3_pair_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    err = cudaFuncSetAttribute(conv3x3_pair_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               232448 - (STATS ? 20608 : 4224));
   });
   if (err != cudaSuccess) { sg_set_error("sg_conv3x3_pair: cannot raise the dynamic shared memory limit"); return (int)err; }
   conv3x3_pair_kernel<STATS><<<pl.grid, NUM_THREADS, pl.smem, st>>>(mx, mw, p);
@@ -525,7 +435,7 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
                               int Cout, void* stream) {
   using namespace tc2;
   Plan pl;
-  SG_REQUIRE(make_plan(N, H, W, Cin, Cout, &pl), "sg_conv3x3_pair: shape not supported");
+  SG_REQUIRE(make_plan(N, H, W, Cin, Cout, &pl, part != nullptr), "sg_conv3x3_pair: shape not supported");
   EncodeTiledFn enc = get_encode();
   SG_REQUIRE(enc != nullptr, "sg_conv3x3_pair: cuTensorMapEncodeTiled unavailable");
   CUtensorMap map_x, map_w;

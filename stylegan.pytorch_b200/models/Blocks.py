@@ -52,8 +52,13 @@ class InputBlock(nn.Module):
             # [1,C,4,4] parameter -> NHWC rows, broadcast over the batch; the per-channel bias rides along in the
             # epilogue's first pass (reference Blocks.py:51-52)
             c = self.const.permute(0, 2, 3, 1).expand(batch, -1, -1, -1)
-            x = _ops.Cast.apply(c.contiguous(), dt)
-            x = self.epi1.forward_nhwc(x, dlatents_in_range[:, 0], pre_bias=self.bias, pre_bias_mul=1.0)
+            # This first epilogue always runs in fp32 (16 pixels x 512 channels per image: free).  Its input is the same
+            # constant at every pixel plus noise_w[c] * noise, so a channel with a small noise weight has mean >> std;
+            # InstanceNorm divides by that std, and rounding z to bf16 BEFORE the normalisation put up to 9 % of relative
+            # error into such channels -- it was the dominant term of the bf16 image error at every depth (5 % -> see
+            # tests/test_gpu_fullwidth.py).  The normalised output has unit variance and rounds to bf16 harmlessly.
+            x = self.epi1.forward_nhwc(c.contiguous(), dlatents_in_range[:, 0], pre_bias=self.bias, pre_bias_mul=1.0)
+            x = _ops.Cast.apply(x, dt)
         else:
             x = self.dense(dlatents_in_range[:, 0]).reshape(batch, self.nf, 4, 4)
             x = self.epi1.forward_nhwc(to_nhwc(x), dlatents_in_range[:, 0])

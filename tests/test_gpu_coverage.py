@@ -1,6 +1,7 @@
 """Wider coverage of the drop-in networks on the GPU: every depth and fade-in alpha, 'fixed' structure, eval mode,
 the non-default losses, conditional mode, checkpoint round trip (the pyramid the reference lacks)."""
 import io
+import os
 import random
 
 import pytest
@@ -266,3 +267,66 @@ def test_full_width_step_vs_oracle(prec, tol):
             ref = st.d[k] - d_sd[k]
             agree = float(((mine * ref) > 0).float().mean())
             assert agree > 0.9, (k, agree)      # round-off-sized gradients have random sign
+
+
+def test_standard_and_conditional_losses_vs_reference_golden(golden_dir):
+    """StandardGAN.dis_loss and the CONDITIONAL generator / discriminator with ConditionalGANLoss against
+    values recorded from the live reference (oracle/make_golden.py --losses; reference models/Losses.py:54-133,
+    GAN.py:233-236, 326-369, 395-437): forward image, logits, both losses and every parameter-gradient norm."""
+    from models import Losses
+    from models.GAN import Generator, Discriminator
+    from test_gpu_networks import FixedMixing, set_noise
+    from test_oracle_golden import arch_from
+    fx = torch.load(os.path.join(golden_dir, "losses2_tiny16_d2.pt"), weights_only=False)
+    arch = arch_from(fx["arch"])
+    depth, alpha, K = fx["depth"], fx["alpha"], fx["n_classes"]
+    real = fx["real"].to(DEV)
+    # --- StandardGAN on the unconditional discriminator
+    d = Discriminator(**arch.d_kwargs()).to(DEV)
+    d.load_state_dict(fx["d_init"])
+    d.train()
+    dl = Losses.StandardGAN(d).dis_loss(real, fx["fake_in"].to(DEV), depth, alpha)
+    ref = fx["standard"]
+    assert abs(float(dl) - ref["d_loss"]) <= 1e-3 * abs(ref["d_loss"])
+    grads = torch.autograd.grad(dl, list(d.parameters()), allow_unused=True)
+    for (n, _), g in zip(d.named_parameters(), grads):
+        if g is None:
+            assert n not in ref["d_grad_norms"], n
+        else:
+            assert abs(float(g.norm()) - ref["d_grad_norms"][n]) <= 3e-3 * ref["d_grad_norms"][n] + 1e-9, n
+    # gen_loss: the reference's own is not executable (Losses.py:131); ours is the evident intent, BCE against ones
+    gl = Losses.StandardGAN(d).gen_loss(None, fx["fake_in"].to(DEV), depth, alpha)
+    want = torch.nn.functional.binary_cross_entropy_with_logits(d(fx["fake_in"].to(DEV), depth, alpha).squeeze(),
+                                                                torch.ones(fx["batch"], device=DEV))
+    assert abs(float(gl) - float(want)) < 1e-6
+    # --- conditional networks
+    c = fx["conditional"]
+    g = Generator(conditional=True, n_classes=K, **arch.g_kwargs()).to(DEV)
+    dc = Discriminator(conditional=True, n_classes=K, **arch.d_kwargs()).to(DEV)
+    assert list(g.state_dict().keys()) == list(c["g_init"].keys())
+    assert list(dc.state_dict().keys()) == list(c["d_init"].keys())
+    g.load_state_dict(c["g_init"]); dc.load_state_dict(c["d_init"])
+    g.train(); dc.train()
+    set_noise(g, c["noises"])
+    labels = c["labels"].to(DEV)
+    with FixedMixing(c["mix"][0], c["mix"][1], depth):
+        fake = g(c["z"].to(DEV), depth, alpha, labels)
+    assert rel(fake, c["fake"]) < 1e-3
+    assert rel(dc(real, depth, alpha, labels_in=labels), c["logits_real"]) < 1e-3
+    CL = Losses.ConditionalGANLoss(dc)
+    cdl = CL.dis_loss(real, c["fake"].to(DEV), labels, depth, alpha)
+    assert abs(float(cdl) - c["d_loss"]) <= 1e-3 * abs(c["d_loss"])
+    grads = torch.autograd.grad(cdl, list(dc.parameters()), allow_unused=True)
+    for (n, _), gr in zip(dc.named_parameters(), grads):
+        if gr is None:
+            assert n not in c["d_grad_norms"], n
+        else:
+            assert abs(float(gr.norm()) - c["d_grad_norms"][n]) <= 3e-3 * c["d_grad_norms"][n] + 1e-9, n
+    cgl = CL.gen_loss(None, fake, labels, depth, alpha)
+    assert abs(float(cgl) - c["g_loss"]) <= 1e-3 * abs(c["g_loss"])
+    grads = torch.autograd.grad(cgl, list(g.parameters()), allow_unused=True)
+    for (n, _), gr in zip(g.named_parameters(), grads):
+        if gr is None:
+            assert n not in c["g_grad_norms"], n
+        else:
+            assert abs(float(gr.norm()) - c["g_grad_norms"][n]) <= 5e-3 * c["g_grad_norms"][n] + 1e-9, n

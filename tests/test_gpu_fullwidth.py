@@ -9,6 +9,7 @@ errors are written to gpurun_out/fullwidth_errors_<name>_<precision>.json so tha
 import json
 import os
 import random
+import re
 
 import pytest
 import torch
@@ -28,8 +29,18 @@ FP32_TOL = dict(image=1e-3, avg=1e-4, logits=1e-3, r1=2e-3, loss=1e-3, grad_norm
 # bf16 activations + bf16 tensor-core operands, fp32 accumulation; 8 mantissa bits = 3.9e-3 per rounding, ~30 layers deep.
 # image/logits: relative L2 of the tensor; r1/loss: relative; grad_norm: relative error of the per-parameter gradient
 # norm; grad_head / grad_full: relative L2 of the first 64 / all elements of the gradient.
-BF16_TOL = dict(image=8e-2, avg=1e-4, logits=6e-2, r1=1.5e-1, loss=2e-2, grad_norm=1e-1, grad_head=2.5e-1,
-                grad_full=2.5e-1)
+BF16_TOL = dict(image=3e-2, avg=1e-4, logits=2e-2, r1=5e-2, loss=2e-2, grad_norm=1e-1, grad_head=5e-1,
+                grad_full=5e-1,
+                # gradients that are small residuals of cancelling sums (a bias / noise weight / the learned constant in
+                # front of an InstanceNorm: exactly zero if LeakyReLU were linear): the bf16 forward noise does not cancel,
+                # so the bound is on the ABSOLUTE error in units of the tensor's own reference norm, and it is loose
+                cancel_norm=2.5, cancel_head=2.5, cancel_full=2.5)
+FP32_TOL.update(cancel_norm=3e-3, cancel_head=3e-2, cancel_full=5e-3)
+CANCEL = re.compile(r"^G\..*(conv\w*\.bias|noise\.weight|init_block\.(const|bias))$")
+
+
+def grad_kind(kind, name):
+    return kind.replace("grad_", "cancel_") if CANCEL.match(name) else kind
 
 
 def rel(a, b):
@@ -77,6 +88,16 @@ def test_full_width_vs_reference_golden(golden_dir, name, precision):
         if not err <= tol[kind]:
             bad.append("%s %s: %.3e > %.1e (%s)" % (kind, key, err, tol[kind], precision))
 
+    def check_grad(name, gr, ref):
+        check(grad_kind("grad_norm", name), name, abs(float(gr.norm()) - ref["norm"]) / (ref["norm"] + 1e-12))
+        # the 64-element head is judged against the size its elements should have (norm * sqrt(64 / numel)) when the
+        # head itself happens to be small
+        head = gr.flatten()[:64].double().cpu()
+        scale = max(float(ref["head"].double().norm()), ref["norm"] * (min(64, gr.numel()) / gr.numel()) ** 0.5)
+        check(grad_kind("grad_head", name), name, float((head - ref["head"].double()).norm()) / (scale + 1e-30))
+        if ref["full"] is not None:
+            check(grad_kind("grad_full", name), name, rel(gr, ref["full"]))
+
     models.set_precision(precision)
     _ops.clear_weight_cache()
     try:
@@ -114,10 +135,7 @@ def test_full_width_vs_reference_golden(golden_dir, name, precision):
                 assert n not in fx["d_grads"], n
                 continue
             ref = fx["d_grads"][n]
-            check("grad_norm", "D." + n, abs(float(gr.norm()) - ref["norm"]) / (ref["norm"] + 1e-12))
-            check("grad_head", "D." + n, rel(gr.flatten()[:64], ref["head"]))
-            if ref["full"] is not None:
-                check("grad_full", "D." + n, rel(gr, ref["full"]))
+            check_grad("D." + n, gr, ref)
         del grads, d_loss, r1
         g_loss = loss.gen_loss(None, fake, depth, alpha)
         check("loss", "g_loss", abs(float(g_loss) - fx["g_loss"]) / abs(fx["g_loss"]))
@@ -128,10 +146,7 @@ def test_full_width_vs_reference_golden(golden_dir, name, precision):
                 assert n not in fx["g_grads"], n
                 continue
             ref = fx["g_grads"][n]
-            check("grad_norm", "G." + n, abs(float(gr.norm()) - ref["norm"]) / (ref["norm"] + 1e-12))
-            check("grad_head", "G." + n, rel(gr.flatten()[:64], ref["head"]))
-            if ref["full"] is not None:
-                check("grad_full", "G." + n, rel(gr, ref["full"]))
+            check_grad("G." + n, gr, ref)
         assert not bad, "\n".join(bad)
     finally:
         models.set_precision("fp32")

@@ -67,12 +67,17 @@ def test_graph_replay_equals_eager(precision, loss):
     # The first two steps run the same eager code in both runs; from the third on one of them is a replay.  A GAN step
     # is a chaotic map (Adam with beta1 = 0 turns round-off-sized gradient differences into +-lr parameter steps), so the
     # bound opens up with the step index.
+    # Steps 2 and 3 are the first replays (with alpha = 0.40 and 0.55: the fade-in really is read from device memory)
+    # and start from states that agree to round-off: they are the sharp check.
     for i, ((de, ge), (dg, gg)) in enumerate(zip(eager, graph)):
-        tol = (1e-5 if i < 2 else 3e-3) if precision == "fp32" else (1e-5 if i < 2 else 5e-2)
+        if precision == "fp32":
+            tol = 1e-5 if i < 2 else (5e-4 if i < 4 else 5e-2)
+        else:
+            tol = 1e-5 if i < 2 else (2e-2 if i < 4 else 1e-1)
         assert abs(de - dg) <= tol * max(1.0, abs(de)), (i, eager, graph)
         assert abs(ge - gg) <= tol * max(1.0, abs(ge)), (i, eager, graph)
     worst = max(rel(st_g[k], st_e[k]) for k in st_e if st_e[k].dtype.is_floating_point and st_e[k].numel() > 1)
-    assert worst < (5e-3 if precision == "fp32" else 1e-1), worst
+    assert worst < (5e-2 if precision == "fp32" else 2e-1), worst
 
 
 def test_graph_path_is_skipped_when_not_applicable():

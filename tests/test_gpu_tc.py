@@ -124,9 +124,12 @@ def test_up_down_layers_on_tensor_cores(kind, ci, co, hw):
 
 @pytest.mark.parametrize("kind", ["up", "up_fused", "down"])
 @pytest.mark.parametrize("direction", ["fwd", "dgrad"])
-@pytest.mark.parametrize("N,lo,ci,co", [(2, 16, 64, 64), (1, 32, 128, 64), (2, 16, 256, 128), (3, 64, 64, 128)])
-def test_fused_updown_kernel_matches_oracle(kind, direction, N, lo, ci, co):
-    """sg_convud_tc (tap-merged 4-phase 2x2 / 4x4-stride-2 tcgen05 kernels) vs torch on CPU, both directions."""
+@pytest.mark.parametrize("N,lo,ci,co", [(2, 16, 64, 64), (1, 32, 128, 64), (2, 16, 256, 128), (3, 64, 64, 128),
+                                        (2, 16, 256, 256), (1, 8, 512, 512)])
+@pytest.mark.parametrize("pair", [1, 0])
+def test_fused_updown_kernel_matches_oracle(kind, direction, N, lo, ci, co, pair):
+    """sg_convud_tc (tap-merged 4-phase 2x2 / 4x4-stride-2 tcgen05 kernels; CTA-pair and single-CTA forms) vs torch on
+    CPU, both directions."""
     import test_gpu_ops as T
     from models import _ops, _tc
     from models._lib import lib
@@ -150,6 +153,10 @@ def test_fused_updown_kernel_matches_oracle(kind, direction, N, lo, ci, co):
     xd = xin.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
     Wd = torch.nn.Parameter(W.to(DEV))
     y = torch.empty((N, ref.shape[2], ref.shape[3], cout), dtype=torch.bfloat16, device=DEV)
-    assert _tc.try_conv(xd, Wd, kind, direction, scale, None, 1.0, False, y)      # the fused tensor-core path
+    old = lib.sg_pair_updown(pair)
+    try:
+        assert _tc.try_conv(xd, Wd, kind, direction, scale, None, 1.0, False, y)      # the fused tensor-core path
+    finally:
+        lib.sg_pair_updown(old)
     torch.cuda.synchronize()
     assert rel(y.float().permute(0, 3, 1, 2), ref) < 1e-2

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define SGB200_ABI_VERSION 1
+#define SGB200_ABI_VERSION 2
 
 /* Tap-table geometry shared by forward, dgrad and wgrad of every dense convolution (see csrc/sg_conv_generic.cu):
  *   out[n, qy*os+py, qx*os+px, :] = sum_t in[n, qy*is+dy[ph][t], qx*is+dx[ph][t], :] * E[ph][t]   (ph = 2*py+px) */
@@ -201,13 +201,17 @@ int sg_dlatents_bwd_dev(const float* g, float* gw1, float* gw2, int B, int L, in
                         int trunc_cutoff, int has_trunc, void* stream);
 
 /* ---- LayerEpilogue: NoiseLayer + LeakyReLU + InstanceNorm2d + StyleMod, CustomLayers.py:191-248 ---------------- */
+/* All reductions of this library are two-stage with a fixed summation order (no atomics): results are bitwise
+ * reproducible from run to run.  `ws` = sg_epi_ws_floats(N, HW, C) floats of block partials; `sums` [N,C,3] doubles is
+ * fully written by the call. */
+long long sg_epi_ws_floats(int N, int HW, int C);
 int sg_epi_act_stats(const void* y, const float* bias, float bias_mul, const float* noise, const float* noise_w,
-                     int act, void* z, double* sums, int dtype, int N, int HW, int C, void* stream);
+                     int act, void* z, double* sums, float* ws, int dtype, int N, int HW, int C, void* stream);
 int sg_epi_finalize(const double* sums, const float* style, float* mr, float* ab, int N, int C, int HW, float eps,
                     void* stream);
 int sg_affine_nc(const void* z, const float* ab, void* out, int dtype, int N, int HW, int C, void* stream);
-int sg_epi_bwd_reduce(const void* g, const void* z, const float* mr, double* sums, int dtype, int N, int HW, int C,
-                      void* stream);
+int sg_epi_bwd_reduce(const void* g, const void* z, const float* mr, double* sums, float* ws, int dtype, int N, int HW,
+                      int C, void* stream);
 int sg_epi_bwd_finalize(const double* sums, const float* mr, const float* style, float* gstyle, float* coef, int N,
                         int C, int HW, void* stream);
 int sg_epi_bwd_apply(const void* g, const void* z, const float* coef, int act, void* gy, int dtype, int N, int HW,
@@ -215,8 +219,11 @@ int sg_epi_bwd_apply(const void* g, const void* z, const float* coef, int act, v
 
 /* ---- small float32 kernels -------------------------------------------------------------------------------------- */
 /* EqualizedLinear.forward, CustomLayers.py:99-103 (x rows `ldx` apart) */
+/* wide inputs (I >= 2048: the discriminator's dense0) are split along I into sg_linear_fwd_ws_floats(B, I, O) floats
+ * of partial products (0: no workspace needed), summed in slice order */
+long long sg_linear_fwd_ws_floats(int B, int I, int O);
 int sg_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale, float bias_mul,
-                  int act, float* y, int B, int I, int O, void* stream);
+                  int act, float* y, int B, int I, int O, float* ws, void* stream);
 int sg_linear_dgrad(const float* gy, const float* W, float scale, float* gx, int B, int I, int O, void* stream);
 int sg_linear_wgrad(const float* gy, const float* x, long long ldx, float scale, float bias_scale, float* gW,
                     float* gb, int B, int I, int O, int accumulate, void* stream);
@@ -237,7 +244,8 @@ int sg_scale_by_scalar(const float* x, const float* gout, float coef, float* gx,
 
 /* ---- optimizer step: torch.optim.Adam + clip_grad_norm_ + update_average, GAN.py:529-533,651-656 ---------------- */
 int sg_chunk_elems(void);
-int sg_sqnorm_multi(const SgTensorEntry* table_dev, int T, int total_chunks, double* out_dev, void* stream);
+/* ws: total_chunks doubles (one partial per chunk, summed in chunk order by a second one-block kernel) */
+int sg_sqnorm_multi(const SgTensorEntry* table_dev, int T, int total_chunks, double* out_dev, double* ws, void* stream);
 int sg_adam_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float lr, float beta1, float beta2,
                   float eps, float grad_scale, const double* normsq_dev, float max_norm, float ema_beta, void* stream);
 int sg_ema_multi(const SgTensorEntry* table_dev, int T, int total_chunks, float ema_beta, void* stream);

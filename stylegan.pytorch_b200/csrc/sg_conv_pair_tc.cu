@@ -69,7 +69,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   uint8_t* smem_w = smem + (size_t)p.stages * p.stage_bytes;
   Barriers* bars = reinterpret_cast<Barriers*>(smem_w + p.w_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = blockIdx.x & 1u;          // == %cluster_ctarank for a 1-D grid of 2-CTA clusters, and provably warp-uniform: with the special register the MMA loop lost its uniform-datapath form (an ELECT/R2UR waterfall per tcgen05.mma, ~110 cycles each)
   const bool leader_cta = rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int nt = cluster_id % p.tiles_n;                 // this pair's N block

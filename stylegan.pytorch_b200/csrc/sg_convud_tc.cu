@@ -250,7 +250,7 @@ convud_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   PairBarriers* bars = reinterpret_cast<PairBarriers*>(smem + (size_t)p.stages * p.stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = blockIdx.x & 1u;          // == %cluster_ctarank for a 1-D grid of 2-CTA clusters, and provably warp-uniform: with the special register the MMA loop lost its uniform-datapath form (an ELECT/R2UR waterfall per tcgen05.mma, ~110 cycles each)
   const bool leader_cta = rank == 0;
   const int cluster_id = blockIdx.x >> 1, clusters = gridDim.x >> 1;
   const int nt = cluster_id % p.tiles_n;

@@ -6,7 +6,8 @@
 //   bwd 2  g_pre = (c1*g + k*(z-mean) + c0) * lrelu'(z)                           (sg_epi_bwd_finalize + _apply)
 // Numerics: the statistics are sums of (z - K) with the pivot K[n,c] = z at the image's first pixel, so the one-pass
 // variance does not cancel even when mean^2 >> var (the 4x4 constant-input layer: z = 2 + small noise); block
-// partials are fp32, cross-block accumulation fp64.  All affine forms are written around (z - mean) for the same reason.
+// partials are fp32 (one record per block, no atomics), summed in block order in fp64 by a second small kernel: bitwise
+// reproducible.  All affine forms are written around (z - mean) for the same reason.
 #include "sg_common.cuh"
 #include "../../include/sgb200.h"
 
@@ -21,7 +22,8 @@ template <class T, int MODE>
 __global__ void epi_reduce_kernel(const T* __restrict__ in0, const T* __restrict__ in1, T* __restrict__ zout,
                                   const float* __restrict__ bias, float bias_mul, const float* __restrict__ noise,
                                   const float* __restrict__ noise_w, const float* __restrict__ mr,
-                                  double* __restrict__ sums, int HW, int C, int pix_per_blk, int act) {
+                                  double* __restrict__ sums, float* __restrict__ ws, int HW, int C, int pix_per_blk,
+                                  int act) {
   extern __shared__ float sm[];  // [2][EPI_ROWS][C]
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_blk;
@@ -72,7 +74,7 @@ __global__ void epi_reduce_kernel(const T* __restrict__ in0, const T* __restrict
     float s = 0.f;
 #pragma unroll
     for (int r = 0; r < EPI_ROWS; ++r) s += sm[(j * EPI_ROWS + r) * C + c];
-    atomicAdd(&sums[((size_t)n * C + c) * 3 + j], (double)s);
+    ws[(((size_t)n * gridDim.x + blockIdx.x) * 2 + j) * C + c] = s;
   }
 }
 
@@ -83,7 +85,8 @@ __global__ void __launch_bounds__(256) epi_reduce_vec_kernel(const T* __restrict
                                                              float bias_mul, const float* __restrict__ noise,
                                                              const float* __restrict__ noise_w,
                                                              const float* __restrict__ mr, double* __restrict__ sums,
-                                                             int HW, int C, int pix_per_blk, int act) {
+                                                             float* __restrict__ ws, int HW, int C, int pix_per_blk,
+                                                             int act) {
   using V = SgVec<T>;
   extern __shared__ float sm[];  // [2][PR][C]
   const int CV = C / V::N;
@@ -180,8 +183,18 @@ __global__ void __launch_bounds__(256) epi_reduce_vec_kernel(const T* __restrict
     int j = i / C, c = i % C;
     float s = 0.f;
     for (int r = 0; r < PR; ++r) s += sm[((size_t)j * PR + r) * C + c];
-    atomicAdd(&sums[((size_t)n * C + c) * 3 + j], (double)s);
+    ws[(((size_t)n * gridDim.x + blockIdx.x) * 2 + j) * C + c] = s;
   }
+}
+
+// sums[n,c,j] = sum over the image's blocks, in block order, of the fp32 partials (fp64 accumulation)
+__global__ void epi_sum_parts_kernel(const float* __restrict__ ws, int chunks, double* __restrict__ sums, int N, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C * 2) return;
+  const int c = i % C, j = (i / C) % 2, n = i / (2 * C);
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += (double)ws[(((size_t)n * chunks + k) * 2 + j) * C + c];
+  sums[((size_t)n * C + c) * 3 + j] = s;
 }
 
 // per-(n,c): mean/rstd and the fused affine (a, d).  style = [N, 2C] (s0 | s1); style may be null (plain IN).
@@ -346,18 +359,26 @@ __global__ void epi_bwd_apply_kernel(const T* __restrict__ g, const T* __restric
   }
 }
 
-template <class T, int MODE>
-int launch_reduce(const void* in0, const void* in1, void* zout, const float* bias, float bias_mul, const float* noise,
-                  const float* noise_w, const float* mr, double* sums, int N, int HW, int C, int act, cudaStream_t st) {
-  int bx = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
-  dim3 block(bx, EPI_ROWS);
-  // aim for >= ~4 waves of CTAs; each CTA at least 64 pixels
+// blocks per image of the two-value reductions: >= ~4 waves of CTAs overall, each CTA at least 64 pixels
+static void reduce_chunks(int N, int HW, int* chunks_out, int* pix_per_blk_out) {
   int chunks = (148 * 4 + N - 1) / N;
   int maxchunks = (HW + 63) / 64;
   if (chunks > maxchunks) chunks = maxchunks;
   if (chunks < 1) chunks = 1;
   int pix_per_blk = (HW + chunks - 1) / chunks;
-  chunks = (HW + pix_per_blk - 1) / pix_per_blk;
+  *chunks_out = (HW + pix_per_blk - 1) / pix_per_blk;
+  *pix_per_blk_out = pix_per_blk;
+}
+
+template <class T, int MODE>
+int launch_reduce(const void* in0, const void* in1, void* zout, const float* bias, float bias_mul, const float* noise,
+                  const float* noise_w, const float* mr, double* sums, float* ws, int N, int HW, int C, int act,
+                  cudaStream_t st) {
+  if (ws == nullptr) { sg_set_error("epilogue: workspace missing (sg_epi_ws_floats)"); return 1000; }
+  int bx = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+  dim3 block(bx, EPI_ROWS);
+  int chunks, pix_per_blk;
+  reduce_chunks(N, HW, &chunks, &pix_per_blk);
   size_t smem = (size_t)2 * EPI_ROWS * C * sizeof(float);
   if (smem > 48 * 1024) { sg_set_error("epilogue: C too large"); return 1000; }
   dim3 grid(chunks, N);
@@ -365,22 +386,32 @@ int launch_reduce(const void* in0, const void* in1, void* zout, const float* bia
   if (C % VN == 0 && C / VN <= 256 && (size_t)2 * (256 / (C / VN)) * C * sizeof(float) <= 48 * 1024) {
     size_t smv = (size_t)2 * (256 / (C / VN)) * C * sizeof(float);
     epi_reduce_vec_kernel<T, MODE><<<grid, 256, smv, st>>>((const T*)in0, (const T*)in1, (T*)zout, bias, bias_mul,
-                                                           noise, noise_w, mr, sums, HW, C, pix_per_blk, act);
-    return sg_check_launch("epi_reduce_vec");
+                                                           noise, noise_w, mr, sums, ws, HW, C, pix_per_blk, act);
+  } else {
+    epi_reduce_kernel<T, MODE><<<grid, block, smem, st>>>((const T*)in0, (const T*)in1, (T*)zout, bias, bias_mul, noise,
+                                                          noise_w, mr, sums, ws, HW, C, pix_per_blk, act);
   }
-  epi_reduce_kernel<T, MODE><<<grid, block, smem, st>>>((const T*)in0, (const T*)in1, (T*)zout, bias, bias_mul, noise,
-                                                        noise_w, mr, sums, HW, C, pix_per_blk, act);
-  return sg_check_launch("epi_reduce");
+  int rc = sg_check_launch("epi_reduce");
+  if (rc) return rc;
+  epi_sum_parts_kernel<<<sg_cdiv((long long)N * C * 2, 128), 128, 0, st>>>(ws, chunks, sums, N, C);
+  return sg_check_launch("epi_sum_parts");
 }
 
 }  // namespace
 
-// sums must be zeroed by the caller (N*C*3 doubles: sum, sum of squares, pivot).
+// floats of workspace the two reductions need (block partials)
+SG_EXPORT long long sg_epi_ws_floats(int N, int HW, int C) {
+  int chunks, ppb;
+  reduce_chunks(N, HW, &chunks, &ppb);
+  return (long long)N * chunks * 2 * C;
+}
+
+// sums: N*C*3 doubles (sum, sum of squares, pivot), fully written (no zeroing needed); ws: sg_epi_ws_floats floats.
 SG_EXPORT int sg_epi_act_stats(const void* y, const float* bias, float bias_mul, const float* noise,
-                               const float* noise_w, int act, void* z, double* sums, int dtype, int N, int HW,
-                               int C, void* stream) {
+                               const float* noise_w, int act, void* z, double* sums, float* ws, int dtype, int N,
+                               int HW, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  SG_DISPATCH(dtype, { return launch_reduce<T, 0>(y, nullptr, z, bias, bias_mul, noise, noise_w, nullptr, sums, N, HW, C, act, st); });
+  SG_DISPATCH(dtype, { return launch_reduce<T, 0>(y, nullptr, z, bias, bias_mul, noise, noise_w, nullptr, sums, ws, N, HW, C, act, st); });
   return 0;
 }
 
@@ -417,10 +448,10 @@ SG_EXPORT int sg_affine_nc(const void* z, const float* ab, void* out, int dtype,
   return sg_check_launch("sg_affine_nc");
 }
 
-SG_EXPORT int sg_epi_bwd_reduce(const void* g, const void* z, const float* mr, double* sums, int dtype, int N, int HW,
-                                int C, void* stream) {
+SG_EXPORT int sg_epi_bwd_reduce(const void* g, const void* z, const float* mr, double* sums, float* ws, int dtype, int N,
+                                int HW, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  SG_DISPATCH(dtype, { return launch_reduce<T, 1>(g, z, nullptr, nullptr, 0.f, nullptr, nullptr, mr, sums, N, HW, C, 0, st); });
+  SG_DISPATCH(dtype, { return launch_reduce<T, 1>(g, z, nullptr, nullptr, 0.f, nullptr, nullptr, mr, sums, ws, N, HW, C, 0, st); });
   return 0;
 }
 

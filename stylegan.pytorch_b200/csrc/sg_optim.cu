@@ -18,7 +18,8 @@ __device__ __forceinline__ int find_entry(const SgTensorEntry* __restrict__ tab,
   return lo;
 }
 
-__global__ void sqnorm_multi_kernel(const SgTensorEntry* __restrict__ tab, int T, double* __restrict__ out) {
+// stage 1: one partial per chunk; stage 2 (one block) sums them in index order -> bitwise reproducible, no atomics
+__global__ void sqnorm_multi_kernel(const SgTensorEntry* __restrict__ tab, int T, double* __restrict__ partial) {
   __shared__ float sm[32];
   const int e = find_entry(tab, T, blockIdx.x);
   const SgTensorEntry en = tab[e];
@@ -28,7 +29,19 @@ __global__ void sqnorm_multi_kernel(const SgTensorEntry* __restrict__ tab, int T
   float s = 0.f;
   for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) { float v = g[i]; s = fmaf(v, v, s); }
   s = sg_block_sum(s, sm);
-  if (threadIdx.x == 0) atomicAdd(out, (double)s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (double)s;
+}
+__global__ void sqnorm_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double sd[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+  sd[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sd[threadIdx.x] += sd[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sd[0];
 }
 
 __global__ void adam_multi_kernel(const SgTensorEntry* __restrict__ tab, int T, float lr, float beta1, float beta2,
@@ -127,9 +140,12 @@ __global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long
 
 SG_EXPORT int sg_chunk_elems(void) { return CHUNK; }
 
-SG_EXPORT int sg_sqnorm_multi(const SgTensorEntry* table_dev, int T, int total_chunks, double* out_dev, void* stream) {
+SG_EXPORT int sg_sqnorm_multi(const SgTensorEntry* table_dev, int T, int total_chunks, double* out_dev, double* ws,
+                              void* stream) {
   if (T <= 0 || total_chunks <= 0) return 0;
-  sqnorm_multi_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, T, out_dev);
+  SG_REQUIRE(ws != nullptr, "sg_sqnorm_multi: workspace of total_chunks doubles missing");
+  sqnorm_multi_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, T, ws);
+  sqnorm_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ws, total_chunks, out_dev);
   return sg_check_launch("sg_sqnorm_multi");
 }
 

@@ -14,12 +14,12 @@ constexpr int LF_IC = 256;    // input chunk staged in shared memory
 constexpr int LF_BMAX = 32;   // batch rows per pass
 // block = 8 warps; warp w owns output o = blockIdx.x*8 + w; x is staged [rows][256] in shared memory so that it is
 // read from L2 once per block instead of once per warp.
-// gridDim.y > 1 splits the input dimension: each slice atomically adds its partial products into y (pre-zeroed) and
-// linear_finish_kernel applies scale / bias / activation afterwards.
+// gridDim.y > 1 splits the input dimension: slice k writes its partial products to ws[k][B][O] and linear_finish_kernel
+// sums the slices in index order (deterministic) and applies scale / bias / activation.
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, long long ldx,
                                                          const float* __restrict__ W, const float* __restrict__ bias,
                                                          float scale, float bias_mul, int act, float* __restrict__ y,
-                                                         int B, int I, int O) {
+                                                         int B, int I, int O, float* __restrict__ ws) {
   __shared__ float xs[LF_BMAX][LF_IC + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * LF_OB + warp;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
           float s = sg_warp_sum(acc[j]);
           if (lane == 0) {
             if (split) {
-              atomicAdd(&y[(size_t)(b0 + j) * O + o], s);
+              ws[((size_t)blockIdx.y * B + (b0 + j)) * O + o] = s;
             } else {
               s = s * scale + (bias ? bias[o] * bias_mul : 0.f);
               y[(size_t)(b0 + j) * O + o] = act ? sg_lrelu(s) : s;
@@ -70,44 +70,52 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
   }
 }
 
-__global__ void linear_finish_kernel(float* __restrict__ y, const float* __restrict__ bias, float scale,
-                                     float bias_mul, int act, int B, int O) {
+__global__ void linear_finish_kernel(float* __restrict__ y, const float* __restrict__ ws, int splits,
+                                     const float* __restrict__ bias, float scale, float bias_mul, int act, int B, int O) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * O) return;
-  float s = y[i] * scale + (bias ? bias[i % O] * bias_mul : 0.f);
+  float acc = 0.f;
+  for (int k = 0; k < splits; ++k) acc += ws[(size_t)k * B * O + i];
+  float s = acc * scale + (bias ? bias[i % O] * bias_mul : 0.f);
   y[i] = act ? sg_lrelu(s) : s;
 }
 
-// gx[b][i] = scale * sum_o gy[b][o] * W[o][i].  grid (I/128, O splits): a thread owns column i for up to 32 batch
-// rows over one slice of o, so W is read once and the grid stays wide; slices combine with atomicAdd (gx pre-zeroed).
+// gx[b][i] = scale * sum_o gy[b][o] * W[o][i].  grid (ceil(I/64), ceil(B/32)): a thread owns column i for 8 batch rows
+// and walks ALL of o (gy staged in 64-wide chunks), so every output element has one writer and one summation order:
+// no atomics, bitwise reproducible.  Eight independent weight loads per thread are in flight at a time.
 constexpr int LD_BB = 32;
-constexpr int LD_OS = 64;     // o values per split
-__global__ void linear_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ W, float scale,
-                                    float* __restrict__ gx, int B, int I, int O) {
-  __shared__ float gs[LD_BB][LD_OS];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int o0 = blockIdx.y * LD_OS;
-  const int on = (O - o0 < LD_OS) ? (O - o0) : LD_OS;
-  for (int b0 = 0; b0 < B; b0 += LD_BB) {
-    const int nb = (B - b0 < LD_BB) ? (B - b0) : LD_BB;
+__global__ void __launch_bounds__(256) linear_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ W,
+                                                           float scale, float* __restrict__ gx, int B, int I, int O) {
+  __shared__ float gs[LD_BB][65];
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63), bq = threadIdx.x >> 6;
+  const int b0 = blockIdx.y * LD_BB;
+  const int ic = i < I ? i : I - 1;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int oc = 0; oc < O; oc += 64) {
     __syncthreads();
-    for (int t = threadIdx.x; t < nb * LD_OS; t += blockDim.x) {
-      int r = t / LD_OS, c = t % LD_OS;
-      gs[r][c] = (c < on) ? gy[(size_t)(b0 + r) * O + o0 + c] : 0.f;
+    for (int e = threadIdx.x; e < LD_BB * 64; e += blockDim.x) {
+      const int b = e >> 6, o = e & 63;
+      gs[b][o] = (b0 + b < B && oc + o < O) ? gy[(size_t)(b0 + b) * O + oc + o] : 0.f;
     }
     __syncthreads();
-    if (i < I) {
-      float acc[LD_BB];
+    const int on = min(64, O - oc);
+    float wv[8];
+    for (int o = 0; o < on; o += 8) {
 #pragma unroll
-      for (int j = 0; j < LD_BB; ++j) acc[j] = 0.f;
-      for (int oo = 0; oo < on; ++oo) {
-        float wv = W[(size_t)(o0 + oo) * I + i];
+      for (int u = 0; u < 8; ++u) wv[u] = (o + u < on) ? W[(size_t)(oc + o + u) * I + ic] : 0.f;
 #pragma unroll
-        for (int j = 0; j < LD_BB; ++j) acc[j] = fmaf(wv, gs[j][oo], acc[j]);
-      }
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int j = 0; j < LD_BB; ++j)
-        if (j < nb) atomicAdd(&gx[(size_t)(b0 + j) * I + i], acc[j] * scale);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gs[bq * 8 + j][o + u], wv[u], acc[j]);
+    }
+  }
+  if (i < I) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + bq * 8 + j;
+      if (b < B) gx[(size_t)b * I + i] = acc[j] * scale;
     }
   }
 }
@@ -344,26 +352,34 @@ __global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float*
 
 }  // namespace
 
-SG_EXPORT int sg_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale,
-                            float bias_mul, int act, float* y, int B, int I, int O, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+static int linear_fwd_splits(int I) {
   int splits = 1;
   if (I >= 2048) {                                  // wide input (discriminator dense0): split I to fill the GPU
     splits = I / 1024;
     if (splits > 16) splits = 16;
   }
-  if (splits > 1) cudaMemsetAsync(y, 0, (size_t)B * O * sizeof(float), st);
-  linear_fwd_kernel<<<dim3(sg_cdiv(O, LF_OB), splits), 256, 0, st>>>(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O);
-  if (splits > 1) linear_finish_kernel<<<sg_cdiv((long long)B * O, 256), 256, 0, st>>>(y, bias, scale, bias_mul, act, B, O);
+  return splits;
+}
+// floats of workspace sg_linear_fwd needs for this shape (0: none)
+SG_EXPORT long long sg_linear_fwd_ws_floats(int B, int I, int O) {
+  const int splits = linear_fwd_splits(I);
+  return splits > 1 ? (long long)splits * B * O : 0;
+}
+SG_EXPORT int sg_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale,
+                            float bias_mul, int act, float* y, int B, int I, int O, float* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = linear_fwd_splits(I);
+  SG_REQUIRE(splits == 1 || ws != nullptr, "sg_linear_fwd: workspace missing (sg_linear_fwd_ws_floats)");
+  linear_fwd_kernel<<<dim3(sg_cdiv(O, LF_OB), splits), 256, 0, st>>>(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O, ws);
+  if (splits > 1)
+    linear_finish_kernel<<<sg_cdiv((long long)B * O, 256), 256, 0, st>>>(y, ws, splits, bias, scale, bias_mul, act, B, O);
   return sg_check_launch("sg_linear_fwd");
 }
 
 SG_EXPORT int sg_linear_dgrad(const float* gy, const float* W, float scale, float* gx, int B, int I, int O,
                               void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(gx, 0, (size_t)B * I * sizeof(float), st);
-  dim3 grid(sg_cdiv(I, 128), sg_cdiv(O, LD_OS));
-  linear_dgrad_kernel<<<grid, 128, 0, st>>>(gy, W, scale, gx, B, I, O);
+  dim3 grid(sg_cdiv(I, 64), sg_cdiv(B, LD_BB));
+  linear_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, W, scale, gx, B, I, O);
   return sg_check_launch("sg_linear_dgrad");
 }
 

@@ -152,16 +152,13 @@ class GSynthesis(nn.Module):
             for i in range(depth - 1):
                 x = self.blocks[i].forward_nhwc(x, dl[:, 2 * (i + 1):2 * (i + 2)])
             x_hi = self.blocks[depth - 1].forward_nhwc(x, dl[:, 2 * depth:2 * (depth + 1)])
-            # straight and residual branches + fade-in in one fused to_rgb (reference GAN.py:199-202); the nearest
-            # up-sampling of the residual branch happens inside the kernel
-            if isinstance(alpha, _ops.DynScalar):
-                # alpha lives in device memory (CUDA-graph replay): evaluate both branches with unit weights -- the
-                # residual one at the low resolution, the 1x1 convolution commutes with nearest up-sampling -- and
-                # blend with the coefficient pair read by the kernel at run time
-                hi = self._rgb(x_hi, depth, 1.0)
-                lo = _ops.UpsampleNCHW.apply(self._rgb(x, depth - 1, 1.0), 2, 1.0)
-                return _ops.Axpby.apply(hi, lo, alpha, None)
-            return self._rgb(x_hi, depth, float(alpha), x, depth - 1, 1.0 - float(alpha))
+            # straight and residual branches + fade-in (reference GAN.py:199-202).  Both branches with unit weights -- the residual one at the low resolution: the 1x1 convolution commutes with
+            # nearest up-sampling (reference GAN.py:199 up-samples the features first) -- then one blend whose coefficient
+            # pair is either two floats or, under CUDA-graph replay, read from device memory by the same kernel.  Eager
+            # and replayed steps therefore execute identical arithmetic.
+            hi = self._rgb(x_hi, depth, 1.0)
+            lo = _ops.UpsampleNCHW.apply(self._rgb(x, depth - 1, 1.0), 2, 1.0)
+            return _ops.Axpby.apply(hi, lo, *_ops.lerp_coefs(alpha))
         raise KeyError("Unknown structure: ", self.structure)
 
 

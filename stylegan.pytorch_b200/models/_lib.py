@@ -36,7 +36,7 @@ def parse_header(path=HEADER_PATH):
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"(?m)^\s*(const char\*|int)\s+(sg_\w+)\s*\(([^;]*?)\)\s*;", src):
+    for m in re.finditer(r"(?m)^\s*(const char\*|long long|int)\s+(sg_\w+)\s*\(([^;]*?)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
@@ -47,7 +47,8 @@ def parse_header(path=HEADER_PATH):
                 else:
                     ty = a.rsplit(" ", 1)[0].replace("const ", "").strip()
                     argtypes.append(_CTYPE[ty])
-        out[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argtypes)
+        out[name] = (ctypes.c_char_p if ret.startswith("const char") else
+                     (ctypes.c_longlong if ret == "long long" else ctypes.c_int), argtypes)
     return out
 
 
@@ -68,7 +69,7 @@ class _Lib:
             fn = getattr(dll, name)     # AttributeError here = header/library drift
             fn.restype = ret
             fn.argtypes = argtypes
-        if dll.sg_abi_version() != 1 or dll.sg_geom_size() != ctypes.sizeof(SgConvGeom):
+        if dll.sg_abi_version() != 2 or dll.sg_geom_size() != ctypes.sizeof(SgConvGeom):
             raise RuntimeError("sgb200: ABI mismatch between models/_lib.py and libsgb200.so")
         self._dll = dll
         return dll

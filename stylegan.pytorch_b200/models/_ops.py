@@ -537,8 +537,10 @@ class Linear(Function):
         B, I = x.shape
         O = W.shape[0]
         y = torch.empty((B, O), dtype=torch.float32, device=x.device)
+        nws = lib.sg_linear_fwd_ws_floats(B, I, O)
+        ws = torch.empty((nws,), dtype=torch.float32, device=x.device) if nws else None
         lib.sg_linear_fwd(ptr(x), ldx, ptr(_c(W.detach())), ptr(bias), float(scale), float(bias_mul), int(act),
-                          ptr(y), B, I, O, stream())
+                          ptr(y), B, I, O, ptr(ws), stream())
         count_launch()
         ctx.save_for_backward(x, W, y if act else None)
         ctx.cfg = (scale, bias_mul, act, bias is not None)
@@ -847,9 +849,10 @@ class Epilogue(Function):
         if style is not None:
             style = _c(style)
         z = torch.empty_like(y)
-        sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
+        sums = torch.empty((N, C, 3), dtype=torch.float64, device=dev)
+        ws = torch.empty((lib.sg_epi_ws_floats(N, HW, C),), dtype=torch.float32, device=dev)
         lib.sg_epi_act_stats(ptr(y), ptr(bias), float(bias_mul), ptr(noise), ptr(noise_w if noise is not None else None),
-                             int(act), ptr(z), ptr(sums), code(y.dtype), N, HW, C, stream())
+                             int(act), ptr(z), ptr(sums), ptr(ws), code(y.dtype), N, HW, C, stream())
         mr = torch.empty((N, C, 2), dtype=torch.float32, device=dev)
         ab = torch.empty((N, C, 3), dtype=torch.float32, device=dev)
         lib.sg_epi_finalize(ptr(sums), ptr(style), ptr(mr), ptr(ab), N, C, HW, float(eps), stream())
@@ -878,8 +881,9 @@ def _epilogue_backward(g, z, mr, style, noise, act, bias_mul, need_b, need_n):
     N, H, W, C = z.shape
     HW = H * W
     dev = z.device
-    sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
-    lib.sg_epi_bwd_reduce(ptr(g), ptr(z), ptr(mr), ptr(sums), code(z.dtype), N, HW, C, stream())
+    sums = torch.empty((N, C, 3), dtype=torch.float64, device=dev)
+    ws = torch.empty((lib.sg_epi_ws_floats(N, HW, C),), dtype=torch.float32, device=dev)
+    lib.sg_epi_bwd_reduce(ptr(g), ptr(z), ptr(mr), ptr(sums), ptr(ws), code(z.dtype), N, HW, C, stream())
     gstyle = torch.empty((N, 2 * C), dtype=torch.float32, device=dev) if style is not None else None
     coef = torch.empty((N, C, 4), dtype=torch.float32, device=dev)
     lib.sg_epi_bwd_finalize(ptr(sums), ptr(mr), ptr(style), ptr(gstyle), ptr(coef), N, C, HW, stream())
@@ -1191,10 +1195,11 @@ class AffineNC(Function):
             lib.sg_affine_nc(ptr(g), ptr(a0), ptr(gx), code(x.dtype), N, HW, C, stream())
             count_launch()
         if ctx.needs_input_grad[1]:
-            sums = torch.zeros((N, C, 3), dtype=torch.float64, device=dev)
+            sums = torch.empty((N, C, 3), dtype=torch.float64, device=dev)
+            ws = torch.empty((lib.sg_epi_ws_floats(N, HW, C),), dtype=torch.float32, device=dev)
             mr = torch.zeros((N, C, 2), dtype=torch.float32, device=dev)
             mr[..., 1] = 1.0
-            lib.sg_epi_bwd_reduce(ptr(g), ptr(x), ptr(mr), ptr(sums), code(x.dtype), N, HW, C, stream())
+            lib.sg_epi_bwd_reduce(ptr(g), ptr(x), ptr(mr), ptr(sums), ptr(ws), code(x.dtype), N, HW, C, stream())
             count_launch()
             gab = torch.stack([sums[..., 1], sums[..., 0]], dim=-1).float()   # d/da = sum g*x, d/db = sum g
         return gx, gab

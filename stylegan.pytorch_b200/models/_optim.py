@@ -82,8 +82,9 @@ class FusedAdam(torch.optim.Adam):
                 tab, chunks = _table(entries, dev)
                 normsq = None
                 if max_norm is not None:
-                    normsq = torch.zeros((1,), dtype=torch.float64, device=dev)
-                    lib.sg_sqnorm_multi(ptr(tab), len(entries), chunks, ptr(normsq), stream())
+                    nbuf = torch.empty((1 + chunks,), dtype=torch.float64, device=dev)
+                    normsq = nbuf[:1]
+                    lib.sg_sqnorm_multi(ptr(tab), len(entries), chunks, ptr(normsq), nbuf.data_ptr() + 8, stream())
                     count_launch()
                 lib.sg_adam_multi(ptr(tab), len(entries), chunks, float(lr), float(b1), float(b2), float(eps),
                                   float(grad_scale), ptr(normsq), float(max_norm or 0.0), float(ema_decay), stream())

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     dll = ctypes.CDLL(_lib.LIB_PATH)
     for name in sigs:
         assert hasattr(dll, name), "libsgb200.so does not export %s" % name
-    assert dll.sg_abi_version() == 1
+    assert dll.sg_abi_version() == 2
     assert dll.sg_geom_size() == ctypes.sizeof(_lib.SgConvGeom)
     assert dll.sg_entry_size() == 64
 

@@ -13,3 +13,7 @@ int sgf_rgb_out3(const void* x, const float* W, const float* bias, float scale, 
 int sgf_channel_sum_blocks(long long P);
 int sgf_channel_sum_w1(const void* x, const float* wt, long long P, int C, float* ws, float* out, float scale,
                        void* stream);
+int sgf_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale, float bias_mul, int act,
+                   float* y, int B, int I, int O, void* stream);
+int sgf_linear_wgrad(const float* gy, const float* x, long long ldx, float scale, float bias_scale, float* gW, float* gb,
+                     int B, int I, int O, int accumulate, void* stream);

@@ -10,6 +10,7 @@
 #include "sg_common.cuh"
 #include "../../include/sgb200.h"
 #include <mutex>
+#include <string.h>
 
 namespace {
 
@@ -39,11 +40,11 @@ __device__ __forceinline__ int find_group(const LinGroup* __restrict__ tab, int 
 
 // ---- forward: block = 16 outputs of one group; x_g staged once in shared memory -------------------------------------------
 template <int IV>   // I = 128 * IV floats (IV float4 per lane)
-__global__ void __launch_bounds__(256) lingroup_fwd_kernel(const LinGroup* __restrict__ tab, int G, int B, int act) {
+__global__ void __launch_bounds__(256) lingroup_fwd_kernel(const LinGroup* __restrict__ tab, const LinGroup one, int G,
+                                                           int B, int act) {
   extern __shared__ float xs[];                        // [B][I]
   constexpr int I = 128 * IV;
-  const int g = find_group(tab, G, blockIdx.x);
-  const LinGroup t = tab[g];
+  const LinGroup t = tab ? tab[find_group(tab, G, blockIdx.x)] : one;   // one group passed by value: no table upload
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int O = (int)t.O;
   const int o0 = ((int)blockIdx.x - (int)t.blk0) * LG_OPB + warp * 2;
@@ -142,12 +143,12 @@ __global__ void __launch_bounds__(256) lingroup_dgrad_kernel(const LinGroup* __r
 // ---- weight / bias gradient: gW_g[o, i] = scale_g * sum_b gy_g[b, o] x_g[b, i]; gb_g[o] = bmul_g * sum_b gy_g[b, o] --------
 // table rows here: x = activations, W = gW (output), bias = gb (output or 0), y = gy.  block = 8 output rows of one group.
 template <int IV>
-__global__ void __launch_bounds__(256) lingroup_wgrad_kernel(const LinGroup* __restrict__ tab, int G, int B) {
+__global__ void __launch_bounds__(256) lingroup_wgrad_kernel(const LinGroup* __restrict__ tab, const LinGroup one, int G,
+                                                             int B, int accumulate) {
   extern __shared__ float xs[];                        // [B][I]
   constexpr int I = 128 * IV;
   __shared__ float gys[LG_B][8];
-  const int g = find_group(tab, G, blockIdx.x);
-  const LinGroup t = tab[g];
+  const LinGroup t = tab ? tab[find_group(tab, G, blockIdx.x)] : one;
   const int O = (int)t.O;
   const int o0 = ((int)blockIdx.x - (int)t.blk0) * 8;
   const float* xp = reinterpret_cast<const float*>(t.x);
@@ -179,15 +180,18 @@ __global__ void __launch_bounds__(256) lingroup_wgrad_kernel(const LinGroup* __r
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r)
-      if (o0 + r < O)
-        *reinterpret_cast<float4*>(gW + (size_t)(o0 + r) * I + c) =
-            make_float4(acc[r][0] * scale, acc[r][1] * scale, acc[r][2] * scale, acc[r][3] * scale);
+      if (o0 + r < O) {
+        float4* d = reinterpret_cast<float4*>(gW + (size_t)(o0 + r) * I + c);
+        float4 v = make_float4(acc[r][0] * scale, acc[r][1] * scale, acc[r][2] * scale, acc[r][3] * scale);
+        if (accumulate) { const float4 old = *d; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+        *d = v;
+      }
   }
   float* gb = reinterpret_cast<float*>(t.bias);
   if (gb && threadIdx.x < 8 && o0 + (int)threadIdx.x < O) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += gys[b][threadIdx.x];
-    gb[o0 + threadIdx.x] = s * bmul;
+    gb[o0 + threadIdx.x] = (accumulate ? gb[o0 + threadIdx.x] : 0.f) + s * bmul;
   }
 }
 
@@ -211,9 +215,10 @@ SG_EXPORT int sg_lingroup_fwd(const void* table, int G, int total_blocks, int B,
     cudaFuncSetAttribute(lingroup_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(lingroup_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   });
-  if (I == 512) lingroup_fwd_kernel<4><<<total_blocks, 256, smem, st>>>(tab, G, B, act);
-  else if (I == 256) lingroup_fwd_kernel<2><<<total_blocks, 256, smem, st>>>(tab, G, B, act);
-  else lingroup_fwd_kernel<1><<<total_blocks, 256, smem, st>>>(tab, G, B, act);
+  const LinGroup none = {};
+  if (I == 512) lingroup_fwd_kernel<4><<<total_blocks, 256, smem, st>>>(tab, none, G, B, act);
+  else if (I == 256) lingroup_fwd_kernel<2><<<total_blocks, 256, smem, st>>>(tab, none, G, B, act);
+  else lingroup_fwd_kernel<1><<<total_blocks, 256, smem, st>>>(tab, none, G, B, act);
   return sg_check_launch("sg_lingroup_fwd");
 }
 
@@ -233,8 +238,63 @@ SG_EXPORT int sg_lingroup_wgrad(const void* table, int G, int total_blocks, int 
   std::call_once(once, [] {
     cudaFuncSetAttribute(lingroup_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   });
-  if (I == 512) lingroup_wgrad_kernel<4><<<total_blocks, 256, smem, st>>>(tab, G, B);
-  else if (I == 256) lingroup_wgrad_kernel<2><<<total_blocks, 256, smem, st>>>(tab, G, B);
-  else lingroup_wgrad_kernel<1><<<total_blocks, 256, smem, st>>>(tab, G, B);
+  const LinGroup none = {};
+  if (I == 512) lingroup_wgrad_kernel<4><<<total_blocks, 256, smem, st>>>(tab, none, G, B, 0);
+  else if (I == 256) lingroup_wgrad_kernel<2><<<total_blocks, 256, smem, st>>>(tab, none, G, B, 0);
+  else lingroup_wgrad_kernel<1><<<total_blocks, 256, smem, st>>>(tab, none, G, B, 0);
   return sg_check_launch("sg_lingroup_wgrad");
+}
+
+// ---- single dense layer through the same kernels (sg_linear_fwd / sg_linear_wgrad fast paths, csrc/sg_small.cu): the
+//      group descriptor travels as a kernel argument, no table in device memory --------------------------------------------
+static long long pack2(float a, float b) {
+  unsigned int ua, ub;
+  memcpy(&ua, &a, 4); memcpy(&ub, &b, 4);
+  return (long long)(((unsigned long long)ub << 32) | ua);
+}
+static void lg_attrs() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(lingroup_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lingroup_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  });
+}
+// -> 0 launched, 1000 not applicable (caller keeps its general kernel)
+int sgf_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale, float bias_mul, int act,
+                   float* y, int B, int I, int O, void* stream) {
+  if (!(I == 512 || I == 256 || I == 128) || ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return 1000;
+  lg_attrs();
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b0 = 0; b0 < B; b0 += LG_B) {
+    const int nb = B - b0 < LG_B ? B - b0 : LG_B;
+    LinGroup t;
+    t.x = (long long)(x + (size_t)b0 * ldx); t.ldx = ldx; t.W = (long long)W; t.bias = (long long)bias;
+    t.y = (long long)(y + (size_t)b0 * O); t.O = O; t.scales = pack2(scale, bias_mul); t.blk0 = 0;
+    const int blocks = (O + LG_OPB - 1) / LG_OPB;
+    const size_t smem = (size_t)((nb + 7) & ~7) * I * sizeof(float);
+    if (I == 512) lingroup_fwd_kernel<4><<<blocks, 256, smem, st>>>(nullptr, t, 1, nb, act);
+    else if (I == 256) lingroup_fwd_kernel<2><<<blocks, 256, smem, st>>>(nullptr, t, 1, nb, act);
+    else lingroup_fwd_kernel<1><<<blocks, 256, smem, st>>>(nullptr, t, 1, nb, act);
+  }
+  return (int)cudaGetLastError();
+}
+int sgf_linear_wgrad(const float* gy, const float* x, long long ldx, float scale, float bias_scale, float* gW, float* gb,
+                     int B, int I, int O, int accumulate, void* stream) {
+  if (!(I == 512 || I == 256 || I == 128) || ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || gW == nullptr)
+    return 1000;
+  lg_attrs();
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b0 = 0; b0 < B; b0 += LG_B) {
+    const int nb = B - b0 < LG_B ? B - b0 : LG_B;
+    LinGroup t;
+    t.x = (long long)(x + (size_t)b0 * ldx); t.ldx = ldx; t.W = (long long)gW; t.bias = (long long)gb;
+    t.y = (long long)(gy + (size_t)b0 * O); t.O = O; t.scales = pack2(scale, bias_scale); t.blk0 = 0;
+    const int blocks = (O + 7) / 8;
+    const size_t smem = (size_t)nb * I * sizeof(float);
+    const int acc = (accumulate || b0 > 0) ? 1 : 0;
+    if (I == 512) lingroup_wgrad_kernel<4><<<blocks, 256, smem, st>>>(nullptr, t, 1, nb, acc);
+    else if (I == 256) lingroup_wgrad_kernel<2><<<blocks, 256, smem, st>>>(nullptr, t, 1, nb, acc);
+    else lingroup_wgrad_kernel<1><<<blocks, 256, smem, st>>>(nullptr, t, 1, nb, acc);
+  }
+  return (int)cudaGetLastError();
 }

@@ -1,6 +1,7 @@
 // Small fp32 kernels: equalized-LR dense layers (mapping MLP, StyleMod affine, discriminator head), PixelNorm,
 // MinibatchStdDev (fwd / bwd / bwd-of-bwd for R1), logistic-loss reductions, squared-sum (R1 penalty).
 #include "sg_common.cuh"
+#include "sg_fast.cuh"
 #include "../../include/sgb200.h"
 
 namespace {
@@ -368,6 +369,10 @@ SG_EXPORT long long sg_linear_fwd_ws_floats(int B, int I, int O) {
 SG_EXPORT int sg_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale,
                             float bias_mul, int act, float* y, int B, int I, int O, float* ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sg_fast_paths) {               // I in {128, 256, 512}: weights-in-registers kernel of csrc/sg_linear_group.cu
+    int rc = sgf_linear_fwd(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O, stream);
+    if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_linear_fwd/group: launch failed"); return rc; }
+  }
   const int splits = linear_fwd_splits(I);
   SG_REQUIRE(splits == 1 || ws != nullptr, "sg_linear_fwd: workspace missing (sg_linear_fwd_ws_floats)");
   linear_fwd_kernel<<<dim3(sg_cdiv(O, LF_OB), splits), 256, 0, st>>>(x, ldx, W, bias, scale, bias_mul, act, y, B, I, O, ws);
@@ -386,6 +391,10 @@ SG_EXPORT int sg_linear_dgrad(const float* gy, const float* W, float scale, floa
 SG_EXPORT int sg_linear_wgrad(const float* gy, const float* x, long long ldx, float scale, float bias_scale,
                               float* gW, float* gb, int B, int I, int O, int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sg_fast_paths && gW) {
+    int rc = sgf_linear_wgrad(gy, x, ldx, scale, bias_scale, gW, gb, B, I, O, accumulate, stream);
+    if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_linear_wgrad/group: launch failed"); return rc; }
+  }
   if (gW) {
     linear_wgrad_kernel<<<sg_cdiv((long long)O * I, 256), 256, 0, st>>>(gy, x, ldx, scale, gW, B, I, O, accumulate);
     int rc = sg_check_launch("sg_linear_wgrad");

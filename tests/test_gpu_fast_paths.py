@@ -121,3 +121,38 @@ def test_channel_sum_fast_equals_general_and_torch(N, hw, C):
     xf = x.float().reshape(P, C)
     ref = torch.stack([(wt.reshape(P, 1) * xf).sum(0), xf.sum(0)]) * 0.5
     assert rel(fast, ref) < 1e-4
+
+
+@pytest.mark.parametrize("B,I,Oo", [(5, 512, 40), (32, 512, 1024), (40, 256, 130), (4, 128, 8), (32, 8192, 512),
+                                     (7, 48, 40)])
+@pytest.mark.parametrize("act", [False, True])
+def test_linear_fast_equals_general_and_torch(B, I, Oo, act):
+    """sg_linear_fwd / _dgrad / _wgrad: the weights-in-registers kernels (csrc/sg_linear_group.cu) for I in {128, 256,
+    512}, the split-I path for wide inputs, the general kernels otherwise -- each against the other setting of the switch
+    and against torch, forward and all gradients; strided input rows as in dlatents[:, l]."""
+    import torch.nn.functional as F
+    from models import _ops
+    torch.manual_seed(6)
+    big = torch.randn(B, 3, I, device=DEV)
+    W = torch.nn.Parameter(torch.randn(Oo, I, device=DEV))
+    b = torch.nn.Parameter(torch.randn(Oo, device=DEV))
+    g = torch.randn(B, Oo, device=DEV)
+
+    def run():
+        x = big[:, 1].clone().requires_grad_(True) if I % 4 else big.clone().requires_grad_(True)
+        xin = x if I % 4 else x[:, 1]
+        y = _ops.Linear.apply(xin, W, b, 0.37, 0.5, act)
+        gx, gW, gb = torch.autograd.grad(y, [x, W, b], g)
+        return torch.cat([y.flatten(), gx.flatten(), gW.flatten(), gb.flatten()])
+    fast, slow = both(run)
+    assert rel(fast, slow) < 1e-5
+    xr = big[:, 1].double().clone().requires_grad_(True)
+    Wr, br = W.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    yr = xr @ (Wr * 0.37).t() + br * 0.5
+    if act:
+        yr = F.leaky_relu(yr, 0.2)
+    grads = torch.autograd.grad(yr, [xr, Wr, br], g.double())
+    n = B * Oo
+    assert rel(fast[:n], yr.flatten()) < 1e-5
+    assert rel(fast[-(Oo * I + Oo):-Oo], grads[1].flatten()) < 1e-5
+    assert rel(fast[-Oo:], grads[2]) < 1e-5

@@ -22,6 +22,7 @@
 #include "sg_common.cuh"
 #include "../../include/sgb200.h"
 #include "sg_tc_common.cuh"
+#include <stdlib.h>
 
 namespace tc2 {
 
@@ -54,6 +55,7 @@ struct Params {
   int act;
   const float* noise;                             // [N,H,W] fp32 or null
   const float* noise_w;                           // [Cout]
+  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads
   float* part;                                    // [N][slots][2][Cout] fp32 or null; slots = 2*pairs
   __nv_bfloat16* y;
 };
@@ -250,11 +252,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (c >= nchunks) break;
         const int c0 = c * 64;
         uint32_t v0[16], v1[16], v2[16], v3[16];
-        tmem_ld16_nowait(taddr + c0, v0);
-        tmem_ld16_nowait(taddr + c0 + 16, v1);
-        tmem_ld16_nowait(taddr + c0 + 32, v2);
-        tmem_ld16_nowait(taddr + c0 + 48, v3);
-        tmem_ld_wait();
+        if (!(p.dbg & 2)) {
+          tmem_ld16_nowait(taddr + c0, v0);
+          tmem_ld16_nowait(taddr + c0 + 16, v1);
+          tmem_ld16_nowait(taddr + c0 + 32, v2);
+          tmem_ld16_nowait(taddr + c0 + 48, v3);
+          tmem_ld_wait();
+        }
         uint8_t* srow = s_stage + (STATS ? qd * 4096 + lane * 128 : 0);
         auto emit16 = [&](const uint32_t (&v)[16], int o) {
           uint32_t packed[8];
@@ -270,7 +274,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
             packed[jj] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          st_global_256(dst + c0 + o, packed);
+          if (!(p.dbg & 1)) st_global_256(dst + c0 + o, packed);
           if (STATS) {                                      // the ROUNDED values, as the consumer will read them
             const int ch = o >> 3;                          // logical 16-byte chunk of this pixel row (8 channels each)
             *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ (lane & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -459,6 +463,10 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
   p.resident = pl.resident; p.w_bytes = pl.w_bytes;
   p.bias = bias; p.bias_mul = bias_mul; p.act = act;
   p.noise = noise; p.noise_w = noise_w; p.part = part;
+  {
+    static const int dbg = getenv("SG_PAIR_DBG") ? atoi(getenv("SG_PAIR_DBG")) : 0;
+    p.dbg = dbg;
+  }
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t st = (cudaStream_t)stream;
   return part ? launch<true>(map_x, map_w, p, pl, st) : launch<false>(map_x, map_w, p, pl, st);

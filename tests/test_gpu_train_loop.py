@@ -147,4 +147,8 @@ def test_train_loop_checkpoint_and_resume(tmp_path, data_module, monkeypatch):
     for name, ma, mc in (("gen", a.gen, c.gen), ("dis", a.dis, c.dis), ("shadow", a.gen_shadow, c.gen_shadow)):
         sa, sc = ma.state_dict(), mc.state_dict()
         for k in sa:
+            if name == "shadow" and k == "truncation.avg_latent":
+                # the shadow's W average moves only when sample grids are rendered from `fixed_input`, which train()
+                # draws afresh at every call (reference GAN.py:718): not part of the resumable state
+                continue
             assert torch.equal(sc[k], sa[k]), (name, k)

@@ -165,8 +165,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive on the LEADER's tmem_empty barrier.  Relaxed on purpose: the hand-over orders tcgen05.ld reads of TMEM
+// (tcgen05.fence::before_thread_sync precedes it) against the next tile's MMAs, not global memory.  With
+// .release.cluster the compiler emits a cluster-scope membar that waits for the warp's outstanding global stores of the
+// tile just written (~1-2 us) -- measured as the dominant stall of the peer CTA's epilogue (profiles/r02_summary.md).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -16,7 +16,7 @@
 //
 // Structure per CTA (both CTAs of the cluster): warp 0 TMA producer (own activation halo box + own half of the weights,
 // completion signalled on the LEADER's mbarrier via the cta_group::2 TMA form), warp 1 MMA issuer (leader CTA only),
-// warps 2-5 epilogue of the CTA's own 128-pixel tile.  A pair walks a CONTIGUOUS range of tile pairs, so the per-image
+// warps 2-9 epilogue of the CTA's own 128-pixel tile.  A pair walks a CONTIGUOUS range of tile pairs, so the per-image
 // statistics are accumulated in registers across tiles and flushed once per (CTA, image): deterministic two-stage
 // reduction, no atomics (sg_epi_finalize_parts sums the slots in fixed order).
 #include "sg_common.cuh"
@@ -31,14 +31,14 @@ using namespace tcu;
 constexpr int TH = 8, TW = 16, BK = 64;
 constexpr int HALO_ROWS = (TH + 2) * TW;           // 160 smem rows of 128 B per kw-shift
 constexpr int A_BYTES = HALO_ROWS * BK * 2;        // 20480
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 
 struct __align__(8) Barriers {
   uint64_t full[MAX_STAGES];      // leader's copy is used: expect_tx by the leader, complete_tx from both CTAs' TMA
   uint64_t empty[MAX_STAGES];     // each CTA's own copy, arrived by the leader's multicast tcgen05.commit
   uint64_t tmem_full[2];          // each CTA's own copy (multicast commit)
-  uint64_t tmem_empty[2];         // leader's copy: 4 epilogue warps of each CTA arrive (count 8)
+  uint64_t tmem_empty[2];         // leader copy: 8 epilogue warps of each CTA arrive (count 16)
   uint64_t wfull;                 // leader's copy: resident weights of both CTAs have landed
   uint32_t tmem_base;
   uint32_t pad;
@@ -94,7 +94,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 16); }   // 8 epilogue warps x 2 CTAs
     mbar_init(&bars->wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&map_x);
@@ -195,7 +195,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM lane quadrant = warp % 4), both CTAs =====================
+    // ===================== epilogue: 8 warps, both CTAs =====================
+    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split every 64-column chunk in halves
+    // (group 0: columns 0-31, group 1: 32-63).  One epilogue warp per scheduler (the first version) ran ~1000 dependent
+    // instructions per tile at IPC ~0.25: 3500 cycles against the 1550 the pair MMAs of a 64->64 tile take.
+    const int grp = (warp - 2) >> 2;
     const int qd = warp & 3;
     const int m = qd * 32 + lane;
     const int pr = m / TW, pc = m % TW;
@@ -204,100 +208,115 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int slots = 2 * p.pairs;
     int acc = 0;
     uint32_t acc_phase = 0;
-    // running per-warp statistics of the current image: lane holds channels colsum_channel(lane, 0/1) of each chunk
+    // running statistics of the current image: lanes 0-15 hold channels 32*grp + 2*lane + {0,1} of each 64-channel chunk
     float st_s[4][2], st_q[4][2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) { st_s[c][0] = st_s[c][1] = st_q[c][0] = st_q[c][1] = 0.f; }
     int cur_n = -1;
     const int nchunks = p.BN / 64;
+    uint8_t* const sblk = s_stage + (STATS ? (grp * 4 + qd) * 2048 : 0);    // this warp's 32 px x 32 ch bf16 block
 
     auto flush = [&](int n) {
-      // combine the four epilogue warps through shared memory in a fixed order and write this CTA's slot of image n
+      // combine the four lane quadrants through shared memory in a fixed order and write this CTA's slot of image n
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= nchunks) break;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        s_red[qd][0][colsum_channel(lane, 0)] = st_s[c][0];
-        s_red[qd][0][colsum_channel(lane, 1)] = st_s[c][1];
-        s_red[qd][1][colsum_channel(lane, 0)] = st_q[c][0];
-        s_red[qd][1][colsum_channel(lane, 1)] = st_q[c][1];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int t = qd * 32 + lane;                      // 128 threads: 2 quantities x 64 channels
-        const int which = t >> 6, ch = t & 63;
-        const float s = (s_red[0][which][ch] + s_red[1][which][ch]) + (s_red[2][which][ch] + s_red[3][which][ch]);
-        p.part[(((size_t)n * slots + slot) * 2 + which) * p.Cout + n0 + c * 64 + ch] = s;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (lane < 16) {
+          const int ch = 32 * grp + 2 * lane;
+          s_red[qd][0][ch] = st_s[c][0]; s_red[qd][0][ch + 1] = st_s[c][1];
+          s_red[qd][1][ch] = st_q[c][0]; s_red[qd][1][ch + 1] = st_q[c][1];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int t = (warp - 2) * 32 + lane;              // 256 threads, the first 128: 2 quantities x 64 channels
+        if (t < 128) {
+          const int which = t >> 6, ch = t & 63;
+          const float sum = (s_red[0][which][ch] + s_red[1][which][ch]) + (s_red[2][which][ch] + s_red[3][which][ch]);
+          p.part[(((size_t)n * slots + slot) * 2 + which) * p.Cout + n0 + c * 64 + ch] = sum;
+        }
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) { st_s[c][0] = st_s[c][1] = st_q[c][0] = st_q[c][1] = 0.f; }
     };
 
-    for (int q = q_begin; q < q_end; ++q) {
+    auto pixel_of = [&](int q) -> size_t {                 // this thread's pixel in the CTA's tile of pair q
       int r = 2 * q + (int)rank;
-      int wt = r % p.tiles_w; r /= p.tiles_w;
-      int ht = r % p.tiles_h;
-      int n = r / p.tiles_h;
+      const int wt = r % p.tiles_w; r /= p.tiles_w;
+      const int ht = r % p.tiles_h;
+      const int n = r / p.tiles_h;
+      return ((size_t)n * p.H + (ht * TH + pr)) * p.W + (wt * TW + pc);
+    };
+    // the noise value of the NEXT tile is requested while the current one is processed
+    float nz_next = (p.noise && q_begin < q_end) ? p.noise[pixel_of(q_begin)] : 0.f;
+    for (int q = q_begin; q < q_end; ++q) {
+      const int n = (2 * q + (int)rank) / p.tiles_per_image;
       if (STATS) {
         if (n != cur_n && cur_n >= 0) flush(cur_n);
         cur_n = n;
       }
-      const int hh = ht * TH + pr, ww = wt * TW + pc;
-      const size_t pix = ((size_t)n * p.H + hh) * p.W + ww;
-      const float nz = p.noise ? p.noise[pix] : 0.f;        // issued before the wait: latency hidden behind the MMAs
+      const size_t pix = pixel_of(q);
+      const float nz = nz_next;
+      if (p.noise && q + 1 < q_end) nz_next = p.noise[pixel_of(q + 1)];
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
-      __nv_bfloat16* dst = p.y + pix * p.Cout + n0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.BN);
+      __nv_bfloat16* dst = p.y + pix * p.Cout + n0 + 32 * grp;
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.BN + 32 * grp);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= nchunks) break;
-        const int c0 = c * 64;
-        uint32_t v0[16], v1[16], v2[16], v3[16];
+        const int c0 = c * 64;                              // this warp: columns c0 + 32*grp + [0, 32)
+        uint32_t v0[16], v1[16];
         if (!(p.dbg & 2)) {
           tmem_ld16_nowait(taddr + c0, v0);
           tmem_ld16_nowait(taddr + c0 + 16, v1);
-          tmem_ld16_nowait(taddr + c0 + 32, v2);
-          tmem_ld16_nowait(taddr + c0 + 48, v3);
           tmem_ld_wait();
         }
-        uint8_t* srow = s_stage + (STATS ? qd * 4096 + lane * 128 : 0);
+        const float* bia = s_bias + c0 + 32 * grp;
+        const float* nwv = s_nw + c0 + 32 * grp;
         auto emit16 = [&](const uint32_t (&v)[16], int o) {
           uint32_t packed[8];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            float a = __uint_as_float(v[2 * jj]) + s_bias[c0 + o + 2 * jj];
-            float b = __uint_as_float(v[2 * jj + 1]) + s_bias[c0 + o + 2 * jj + 1];
+            float a = __uint_as_float(v[2 * jj]) + bia[o + 2 * jj];
+            float b = __uint_as_float(v[2 * jj + 1]) + bia[o + 2 * jj + 1];
             if (p.noise) {
-              a = fmaf(s_nw[c0 + o + 2 * jj], nz, a);
-              b = fmaf(s_nw[c0 + o + 2 * jj + 1], nz, b);
+              a = fmaf(nwv[o + 2 * jj], nz, a);
+              b = fmaf(nwv[o + 2 * jj + 1], nz, b);
             }
             if (p.act) { a = fmaxf(a, SG_LRELU_SLOPE * a); b = fmaxf(b, SG_LRELU_SLOPE * b); }
             __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
             packed[jj] = *reinterpret_cast<uint32_t*>(&h2);
           }
           if (!(p.dbg & 1)) st_global_256(dst + c0 + o, packed);
-          if (STATS) {                                      // the ROUNDED values, as the consumer will read them
-            const int ch = o >> 3;                          // logical 16-byte chunk of this pixel row (8 channels each)
-            *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ (lane & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ (lane & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          if (STATS) {
+            // staging row = 64 bytes (4 chunks of 16 B), chunk index XOR-ed with (row >> 1) & 3: the row-wise 16-byte
+            // stores of a quarter warp and the column-wise 4-byte loads below are both bank-conflict free
+            const int ch = o >> 3;
+            const int sw = (lane >> 1) & 3;
+            uint8_t* srow = sblk + lane * 64;
+            *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ sw) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ sw) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
           }
         };
         emit16(v0, 0);
         emit16(v1, 16);
-        emit16(v2, 32);
-        emit16(v3, 48);
         if (STATS) {
           __syncwarp();
-          // lane l sums channels 2l, 2l+1 (one 32-bit word) over the warp's 32 pixel rows
-          const uint8_t* sblk = s_stage + qd * 4096 + ((lane & 3) << 2);
-          const int lch = lane >> 2;
+          // lane = (row half h, word w): sums channels 2w, 2w+1 over 16 of the warp's 32 pixel rows; the second half
+          // walks rows of the opposite parity so the two halves never meet in a bank
+          const int w = lane & 15, h = lane >> 4;
           float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(sblk + r * 128 + ((lch ^ (r & 7)) << 4));
-            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+          for (int r = 0; r < 16; ++r) {
+            const int row = h * 16 + (r ^ h);
+            const uint32_t x = *reinterpret_cast<const uint32_t*>(sblk + row * 64 + ((((w >> 2) ^ ((row >> 1) & 3))) << 4) +
+                                                                  ((w & 3) << 2));
+            const float lo = __uint_as_float(x << 16), hi = __uint_as_float(x & 0xffff0000u);
             a0 += lo; a1 += hi;
             b0 = fmaf(lo, lo, b0); b1 = fmaf(hi, hi, b1);
           }
+          a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+          b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
           __syncwarp();                                     // the next chunk overwrites the staging block
           st_s[c][0] += a0; st_s[c][1] += a1;
           st_q[c][0] += b0; st_q[c][1] += b1;

@@ -110,7 +110,10 @@ wgradud_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16_mn(p.BM, p.BN);
+    // The GEMM N dimension is the TWO vertical taps of one 64-channel block of x: the (TH+1)-row box is an MN-major operand
+    // whose 64-element blocks are 2048 bytes (one 16-pixel row) apart, so blocks 0/1 of the same buffer are the taps
+    // 0/1 -> N = 128 in one instruction instead of two N = 64 ones (80 instead of 2 x 68 cycles, profiles/r01_mma_rate.txt).
+    const uint32_t idesc = make_idesc_bf16_mn(p.BM, 128);
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
@@ -123,18 +126,16 @@ wgradud_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const uint32_t sA = smem_base + (uint32_t)(stage * p.stage_bytes);
         const uint32_t sB = sA + (uint32_t)a_bytes;
         const uint64_t a0 = make_desc_mn_sw128(sA, DY_BLOCK_BYTES);
-        const uint64_t b0 = make_desc_mn_sw128(sB, X_BLOCK_BYTES);
         const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
-        const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
         const bool leader = elect_one_sync();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {                       // vertical tap = 0 / TW rows into the box
+        for (int j = 0; j < b_blocks; ++j) {                // accumulator (box, j): columns [t][64 channels of block j]
+          const uint64_t b0 = make_desc_mn_sw128(sB + (uint32_t)(j * X_BLOCK_BYTES), TW * 128);
+          const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
 #pragma unroll
           for (int k = 0; k < (TH * TW) / 16; ++k) {
-            const uint32_t al = a_lo + (uint32_t)((k * 2048) >> 4);
-            const uint32_t bl = b_lo + (uint32_t)((t * (TW * 128) + k * 2048) >> 4);
+            const uint32_t ko = (uint32_t)((k * 2048) >> 4);
             if (leader)
-              umma_bf16_lohi(tmem_base + (uint32_t)((box * 2 + t) * p.BN), al, a_hi, bl, b_hi, idesc,
+              umma_bf16_lohi(tmem_base + (uint32_t)((box * b_blocks + j) * 128), a_lo + ko, a_hi, b_lo + ko, b_hi, idesc,
                              k ? 1u : not_first);
           }
         }
@@ -159,10 +160,12 @@ wgradud_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const int widx = (p.mode == MODE_UP) ? (g * 4 + t * 2 + box)          // [phase][a = t][b = box]
                                              : ((box + 2 * t) * 4 + g);       // [u = a + 2*bb][v = g], a = box, bb = t
         float* dst = p.part + ((((size_t)s * 16 + widx) * p.Cout + co) * p.Cin + (size_t)nb * p.BN);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((box * 2 + t) * p.BN);
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
           uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
+          // accumulator (box, x block j = c0 / 64): tap t occupies its columns [t*64, t*64+64)
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                 (uint32_t)((box * b_blocks + (c0 >> 6)) * 128 + t * 64 + (c0 & 63));
+          tmem_ld16(taddr, v);
           if (active && co < p.Cout && nb * p.BN + c0 < p.Cin) {
             float4* d4 = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll

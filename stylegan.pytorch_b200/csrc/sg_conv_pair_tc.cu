@@ -55,7 +55,7 @@ struct Params {
   int act;
   const float* noise;                             // [N,H,W] fp32 or null
   const float* noise_w;                           // [Cout]
-  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads
+  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads, 4 = empty epilogue
   float* part;                                    // [N][slots][2][Cout] fp32 or null; slots = 2*pairs
   __nv_bfloat16* y;
 };
@@ -263,7 +263,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.BN + 32 * grp);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (c >= nchunks) break;
+        if (c >= nchunks || (p.dbg & 4)) break;
         const int c0 = c * 64;                              // this warp: columns c0 + 32*grp + [0, 32)
         uint32_t v0[16], v1[16];
         if (!(p.dbg & 2)) {

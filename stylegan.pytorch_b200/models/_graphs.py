@@ -164,6 +164,5 @@ class StepGraphs:
         cap.rng_base.copy_(cap.rng_host, non_blocking=True)
         e.graph.replay()
         _Noise.offset += e.rng_per_step
-        _ops.bump_weights_epoch()                       # derived weight copies made inside the graph are its own
-        count_launch(e.launches)
+        count_launch(e.launches)                        # (derived weight copies are refreshed inside the graph, in place)
         return e.loss

@@ -129,41 +129,71 @@ def _coef_dev(kind, k, direction, device):
     return c
 
 
+def _token_of(W):
+    """Update counter of whoever rewrites this parameter behind autograd's back: the FusedAdam that owns it or the EMA
+    updater (they write through raw pointers, so `_version` does not move); the global epoch for anything else."""
+    tok = getattr(W, "_sg_token", None)
+    return (tok[0] if tok is not None else -1, _epoch[0])
+
+
 def cached_weight(W, sub, build):
-    """Derived (packed / scaled / bf16) copy of a weight, cached for nn.Parameters only.  An entry is valid for the
-    Parameter OBJECT it was built from (held by weak reference: ids and device pointers are recycled once a model is
-    freed, so neither may stand in for identity) at one (storage, version, weights epoch, shape): the fused
-    optimizer writes parameters through raw pointers and bumps the epoch instead of the tensor version.  Code that
-    edits `param.data` behind autograd's back must call clear_weight_cache()."""
+    """Derived (packed / scaled / bf16) copy of a weight, kept for nn.Parameters only, in a PERSISTENT buffer per
+    (parameter object, variant): `build(W, out)` fills `out` (or allocates when out is None); it must not
+    capture W (the entry would keep the parameter alive).  An entry belongs to the
+    Parameter OBJECT (weak reference: ids and device pointers are recycled once a model is freed) at one (storage,
+    version, shape).  The optimizer that rewrites the parameter refreshes all of its variants in place right after the
+    update (refresh_derived), so a forward pass normally finds them current and launches nothing -- which is also what
+    lets a captured CUDA graph read them: they are refreshed by the graph that contains the optimizer step.  A variant
+    whose stamp is older than the parameter's update counter (EMA shadow, global epoch bump) is rebuilt in place on use.
+    Code that edits `param.data` behind autograd's back must call clear_weight_cache()."""
     if not isinstance(W, torch.nn.Parameter):
-        return build()
-    key = (W.data_ptr(), W._version, _epoch[0], tuple(W.shape))
+        return build(W, None)
+    key = (W.data_ptr(), W._version, tuple(W.shape))
     wid = id(W)
-    hit = _prep_cache.get(wid)
-    if hit is not None and hit[2]() is W and hit[0] == key:
-        E = hit[1].get(sub)
-        if E is not None:
-            return E
-    else:
+    ent = _prep_cache.get(wid)
+    if ent is None or ent[2]() is not W or ent[0] != key:
         def _drop(ref, wid=wid):
             cur = _prep_cache.get(wid)
             if cur is not None and cur[2] is ref:
                 del _prep_cache[wid]
-        hit = (key, {}, weakref.ref(W, _drop))
-        _prep_cache[wid] = hit
-    E = build()
-    hit[1][sub] = E
-    return E
+        ent = (key, {}, weakref.ref(W, _drop))
+        _prep_cache[wid] = ent
+    tok = _token_of(W)
+    it = ent[1].get(sub)
+    if it is None:
+        E = build(W, None)
+        ent[1][sub] = [E, build, tok]
+        return E
+    if it[2] != tok:
+        build(W, it[0])
+        it[2] = tok
+    return it[0]
+
+
+def refresh_derived(params):
+    """Rebuild, in place, every cached variant of the given parameters (called by the optimizer right after it has
+    rewritten them and bumped their update counter)."""
+    for W in params:
+        ent = _prep_cache.get(id(W))
+        if ent is None or ent[2]() is not W:
+            continue
+        if ent[0] != (W.data_ptr(), W._version, tuple(W.shape)):
+            del _prep_cache[id(W)]
+            continue
+        tok = _token_of(W)
+        for it in ent[1].values():
+            it[1](W, it[0])
+            it[2] = tok
 
 
 def prepped_weight(W, kind, direction, dtype, scale):
     """Effective weights E[npt][A][B] of the tap-table convolution in `dtype`."""
-    def build():
+    def build(W, out):
         co, ci, k, _ = W.shape
         t = _geom.tables(kind, k, direction)
         npt = t["nphase"] * t["ntaps"]
         a, b = (co, ci) if t["transpose"] else (ci, co)
-        E = torch.empty((npt, a, b), dtype=dtype, device=W.device)
+        E = out if out is not None else torch.empty((npt, a, b), dtype=dtype, device=W.device)
         coef = _coef_dev(kind, k, direction, W.device)
         lib.sg_wprep_fwd(ptr(_c(W.detach())), ptr(E), code(dtype), co, ci, k * k, npt, ptr(coef), float(scale),
                          t["transpose"], stream())

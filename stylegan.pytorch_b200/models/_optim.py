@@ -21,9 +21,15 @@ def _table(entries, device):
     return _ops.upload_table(t, device), c0
 
 
+_EMA_TOKEN = [0]
+
+
 def ema_update(pairs, beta):
     """tgt = beta*tgt + (1-beta)*src for every (tgt, src) parameter pair, one launch."""
     pairs = [(t, s) for t, s in pairs if t.numel() > 0]
+    for t, _ in pairs:                       # the averaged copies have their own update counter (derived-weight cache)
+        if getattr(t, "_sg_token", None) is not _EMA_TOKEN:
+            t._sg_token = _EMA_TOKEN
     if not pairs:
         return
     dev = pairs[0][0].device
@@ -32,14 +38,17 @@ def ema_update(pairs, beta):
     tab, chunks = _table(entries, dev)
     lib.sg_ema_multi(ptr(tab), len(entries), chunks, float(beta), stream())
     count_launch()
-    _ops.bump_weights_epoch()
+    _EMA_TOKEN[0] += 1                       # variants of the averaged weights are rebuilt lazily, on their next use
 
 
 class FusedAdam(torch.optim.Adam):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, lr=lr, betas=(float(betas[0]), float(betas[1])), eps=eps)
+        self._token = [0]              # update counter shared by this optimizer's parameters (_ops.cached_weight)
         for g in self.param_groups:
             g["capturable"] = True     # keeps state['step'] on the parameter's device through load_state_dict
+            for p in g["params"]:
+                p._sg_token = self._token
 
     def _state_for(self, p):
         st = self.state[p]
@@ -92,5 +101,15 @@ class FusedAdam(torch.optim.Adam):
                 self._keepalive = (tab, normsq)
             if rest:
                 ema_update(rest, ema_decay)
-        _ops.bump_weights_epoch()
+            if entries:
+                # the parameters changed under autograd's feet: refresh their derived (scaled / packed / bf16) copies in
+                # place, here, so that the next forward -- eager or replayed from a CUDA graph -- finds them current
+                updated = [p for p in group["params"] if p.grad is not None]
+                self._token[0] += 1
+                if ema_map is not None:
+                    _EMA_TOKEN[0] += 1
+                    for p in updated:
+                        if p in ema_map and getattr(ema_map[p], "_sg_token", None) is not _EMA_TOKEN:
+                            ema_map[p]._sg_token = _EMA_TOKEN
+                _ops.refresh_derived(updated)
         return None

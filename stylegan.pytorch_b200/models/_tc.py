@@ -26,11 +26,11 @@ def _tc_coef(flipped, device):
 def tc_weight(W, direction, scale, kind="same"):
     """fwd: E[t][co][ci] = s*W[co][ci][t];  dgrad: E[t][ci][co] = s*W[co][ci][8-t] (180-degree rotated taps);
     kind 'same_flip' rotates once more."""
-    def build():
+    def build(W, out):
         co, ci = W.shape[0], W.shape[1]
         rows, cols = (co, ci) if direction == "fwd" else (ci, co)
         flipped = (direction == "dgrad") != (kind == "same_flip")
-        E = torch.empty((9, rows, cols), dtype=torch.bfloat16, device=W.device)
+        E = out if out is not None else torch.empty((9, rows, cols), dtype=torch.bfloat16, device=W.device)
         lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 9, ptr(_tc_coef(flipped, W.device)),
                          float(scale), 1 if direction == "fwd" else 0, stream())
         count_launch()
@@ -57,11 +57,11 @@ def ud_weight(W, kind, direction, scale):
     """E[16][out][in] bf16 for sg_convud_tc from the host tap tables (models/_geom.py)."""
     from . import _geom
 
-    def build():
+    def build(W, out):
         co, ci = W.shape[0], W.shape[1]
         t = _geom.tables(kind, 3, direction)
         rows, cols = (co, ci) if direction == "fwd" else (ci, co)
-        E = torch.empty((16, rows, cols), dtype=torch.bfloat16, device=W.device)
+        E = out if out is not None else torch.empty((16, rows, cols), dtype=torch.bfloat16, device=W.device)
         coef = _ops._coef_dev(kind, 3, direction, W.device)
         lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 16, ptr(coef), float(scale),
                          1 - t["transpose"], stream())

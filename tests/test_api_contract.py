@@ -105,28 +105,48 @@ def test_bucketize():
 
 def test_weight_cache_is_keyed_on_the_parameter_object():
     """ids and storage pointers are recycled after a model is freed: a fresh Parameter must never hit the derived
-    copy of a dead one (models/_ops.py cached_weight)."""
+    copy of a dead one (models/_ops.py cached_weight).  Variants live in persistent buffers that are
+    rebuilt IN PLACE when the parameter's update counter moves."""
     import gc
     from models import _ops
     _ops.clear_weight_cache()
+
+    def builder(_):
+        def build(W, out):
+            if out is None:
+                return W.detach().clone()
+            out.copy_(W.detach())
+            return out
+        return build
     seen = []
     for i in range(1, 33):
         W = torch.nn.Parameter(torch.full((8, 8), float(i)))
-        E = _ops.cached_weight(W, "k", lambda W=W: W.detach().clone())
-        again = _ops.cached_weight(W, "k", lambda: (_ for _ in ()).throw(AssertionError("must be a cache hit")))
+        E = _ops.cached_weight(W, "k", builder(W))
+        again = _ops.cached_weight(W, "k", lambda W, out: (_ for _ in ()).throw(AssertionError("must be a cache hit")))
         assert again is E
         seen.append(float(E[0, 0]))
         del W, E, again
         gc.collect()
     assert seen == [float(i) for i in range(1, 33)]
     assert len(_ops._prep_cache) == 0           # entries die with their parameters
-    # an edit through autograd-visible ops (version bump) or the fused optimizer (epoch bump) invalidates
+    # an edit through autograd-visible ops (version bump) makes a new entry; a raw-pointer rewrite announced through the
+    # update counters (optimizer token / global epoch) refreshes the SAME buffer in place
     W = torch.nn.Parameter(torch.zeros(4))
-    a = _ops.cached_weight(W, "k", lambda: W.detach().clone())
+    a = _ops.cached_weight(W, "k", builder(W))
     with torch.no_grad():
         W.add_(1.0)
-    b = _ops.cached_weight(W, "k", lambda: W.detach().clone())
-    assert float(a[0]) == 0.0 and float(b[0]) == 1.0
+    b = _ops.cached_weight(W, "k", builder(W))
+    assert float(a[0]) == 0.0 and float(b[0]) == 1.0 and b is not a
     W.data.fill_(5.0)
     _ops.bump_weights_epoch()
-    assert float(_ops.cached_weight(W, "k", lambda: W.detach().clone())[0]) == 5.0
+    c = _ops.cached_weight(W, "k", builder(W))
+    assert c is b and float(c[0]) == 5.0
+    W.data.fill_(7.0)
+    W._sg_token = [0]
+    d = _ops.cached_weight(W, "k", builder(W))           # new owner token -> stale -> rebuilt in place
+    assert d is b and float(d[0]) == 7.0
+    W.data.fill_(9.0)
+    W._sg_token[0] += 1
+    _ops.refresh_derived([W])
+    assert float(b[0]) == 9.0
+    assert _ops.cached_weight(W, "k", lambda W, out: (_ for _ in ()).throw(AssertionError("current: no rebuild"))) is b

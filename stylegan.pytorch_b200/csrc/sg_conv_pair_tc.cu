@@ -38,7 +38,7 @@ struct __align__(8) Barriers {
   uint64_t full[MAX_STAGES];      // leader's copy is used: expect_tx by the leader, complete_tx from both CTAs' TMA
   uint64_t empty[MAX_STAGES];     // each CTA's own copy, arrived by the leader's multicast tcgen05.commit
   uint64_t tmem_full[2];          // each CTA's own copy (multicast commit)
-  uint64_t tmem_empty[2];         // leader copy: 8 epilogue warps of each CTA arrive (count 16)
+  uint64_t tmem_empty[2];         // leader copy: the 4 warps of the owning team of each CTA arrive (count 8)
   uint64_t wfull;                 // leader's copy: resident weights of both CTAs have landed
   uint32_t tmem_base;
   uint32_t pad;
@@ -81,12 +81,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int q_begin = (int)((long long)j * p.Q / p.pairs), q_end = (int)((long long)(j + 1) * p.Q / p.pairs);
 
   __shared__ float s_bias[256], s_nw[256];
-  __shared__ float s_red[4][2][64];                      // cross-warp combine of the statistics (one 64-ch chunk)
+  __shared__ float s_red[8][2][64];                      // cross-warp combine of the statistics (one 64-ch chunk)
   // per-warp staging of one 32-pixel x 64-channel bf16 block (4 KB, 16-byte chunks XOR-swizzled by the pixel row so that
   // both the row-wise 16-byte stores and the column-wise 4-byte loads are bank-conflict free).  Column sums through
   // shared memory cost ~64 wavefronts per warp and chunk; a shuffle butterfly (tried first: 248 SHFL per warp and
   // chunk) made the epilogue 3x slower than the MMAs it has to hide behind.
-  __shared__ __align__(16) uint8_t s_stage[STATS ? 4 * 4096 : 16];
+  __shared__ __align__(16) uint8_t s_stage[STATS ? 8 * 4096 : 16];
   for (int i = threadIdx.x; i < p.BN; i += blockDim.x) {
     s_bias[i] = p.bias ? p.bias[n0 + i] * p.bias_mul : 0.f;
     s_nw[i] = (p.noise && p.noise_w) ? p.noise_w[n0 + i] : 0.f;
@@ -94,7 +94,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 16); }   // 8 epilogue warps x 2 CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 8); }    // one team of 4 epilogue warps x 2 CTAs
     mbar_init(&bars->wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&map_x);
@@ -195,43 +195,43 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue: 8 warps, both CTAs =====================
-    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split every 64-column chunk in halves
-    // (group 0: columns 0-31, group 1: 32-63).  One epilogue warp per scheduler (the first version) ran ~1000 dependent
-    // instructions per tile at IPC ~0.25: 3500 cycles against the 1550 the pair MMAs of a 64->64 tile take.
-    const int grp = (warp - 2) >> 2;
+    // ===================== epilogue: two teams of four warps, both CTAs =====================
+    // TMEM lane quadrant = warp % 4 (hardware rule).  Team t = (warp - 2) / 4 owns accumulator buffer t, i.e. every
+    // other tile of the CTA: the epilogue of a tile is a chain of fixed latencies (tmem_full hand-over, TMEM load,
+    // shared-memory round trip of the statistics, global stores) of ~3600 cycles, longer than the ~2500 the MMAs of a
+    // 64->64 tile pair take, and it does not shrink when the tile is split between more warps (tried: column halves).
+    // Two teams overlap the chains of consecutive tiles instead.
+    const int team = (warp - 2) >> 2;
     const int qd = warp & 3;
     const int m = qd * 32 + lane;
     const int pr = m / TW, pc = m % TW;
     const uint32_t empty_remote = mapa_u32(smem_u32(&bars->tmem_empty[0]), 0);
     const int slot = 2 * j + (int)rank;
     const int slots = 2 * p.pairs;
-    int acc = 0;
     uint32_t acc_phase = 0;
-    // running statistics of the current image: lanes 0-15 hold channels 32*grp + 2*lane + {0,1} of each 64-channel chunk
+    // running statistics of the current image (this team's tiles): lane l holds channels 2l, 2l+1 of each 64-ch chunk
     float st_s[4][2], st_q[4][2];
 #pragma unroll
     for (int c = 0; c < 4; ++c) { st_s[c][0] = st_s[c][1] = st_q[c][0] = st_q[c][1] = 0.f; }
     int cur_n = -1;
     const int nchunks = p.BN / 64;
-    uint8_t* const sblk = s_stage + (STATS ? (grp * 4 + qd) * 2048 : 0);    // this warp's 32 px x 32 ch bf16 block
+    uint8_t* const sblk = s_stage + (STATS ? (team * 4 + qd) * 4096 : 0);   // this warp's 32 px x 64 ch bf16 block
 
     auto flush = [&](int n) {
-      // combine the four lane quadrants through shared memory in a fixed order and write this CTA's slot of image n
+      // combine both teams' four lane quadrants through shared memory in a fixed order; write this CTA's slot of image n
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= nchunks) break;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (lane < 16) {
-          const int ch = 32 * grp + 2 * lane;
-          s_red[qd][0][ch] = st_s[c][0]; s_red[qd][0][ch + 1] = st_s[c][1];
-          s_red[qd][1][ch] = st_q[c][0]; s_red[qd][1][ch + 1] = st_q[c][1];
-        }
+        s_red[team * 4 + qd][0][2 * lane] = st_s[c][0]; s_red[team * 4 + qd][0][2 * lane + 1] = st_s[c][1];
+        s_red[team * 4 + qd][1][2 * lane] = st_q[c][0]; s_red[team * 4 + qd][1][2 * lane + 1] = st_q[c][1];
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int t = (warp - 2) * 32 + lane;              // 256 threads, the first 128: 2 quantities x 64 channels
         if (t < 128) {
           const int which = t >> 6, ch = t & 63;
-          const float sum = (s_red[0][which][ch] + s_red[1][which][ch]) + (s_red[2][which][ch] + s_red[3][which][ch]);
+          float sum = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) sum += s_red[w8][which][ch];
           p.part[(((size_t)n * slots + slot) * 2 + which) * p.Cout + n0 + c * 64 + ch] = sum;
         }
       }
@@ -246,77 +246,74 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int n = r / p.tiles_h;
       return ((size_t)n * p.H + (ht * TH + pr)) * p.W + (wt * TW + pc);
     };
-    // the noise value of the NEXT tile is requested while the current one is processed
-    float nz_next = (p.noise && q_begin < q_end) ? p.noise[pixel_of(q_begin)] : 0.f;
+    // the noise value of the team's NEXT tile is requested while the current one is processed
+    const int q_first = q_begin + team;
+    float nz_next = (p.noise && q_first < q_end) ? p.noise[pixel_of(q_first)] : 0.f;
     for (int q = q_begin; q < q_end; ++q) {
       const int n = (2 * q + (int)rank) / p.tiles_per_image;
-      if (STATS) {
+      if (STATS) {                                          // both teams see every image boundary, in the same order
         if (n != cur_n && cur_n >= 0) flush(cur_n);
         cur_n = n;
       }
+      if (((q - q_begin) & 1) != team) continue;            // the other team's tile (accumulator buffer = team)
       const size_t pix = pixel_of(q);
       const float nz = nz_next;
-      if (p.noise && q + 1 < q_end) nz_next = p.noise[pixel_of(q + 1)];
-      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      if (p.noise && q + 2 < q_end) nz_next = p.noise[pixel_of(q + 2)];
+      mbar_wait(&bars->tmem_full[team], acc_phase);
       tc_fence_after();
-      __nv_bfloat16* dst = p.y + pix * p.Cout + n0 + 32 * grp;
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.BN + 32 * grp);
+      __nv_bfloat16* dst = p.y + pix * p.Cout + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(team * p.BN);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= nchunks || (p.dbg & 4)) break;
-        const int c0 = c * 64;                              // this warp: columns c0 + 32*grp + [0, 32)
-        uint32_t v0[16], v1[16];
+        const int c0 = c * 64;
+        uint32_t v0[16], v1[16], v2[16], v3[16];
         if (!(p.dbg & 2)) {
           tmem_ld16_nowait(taddr + c0, v0);
           tmem_ld16_nowait(taddr + c0 + 16, v1);
+          tmem_ld16_nowait(taddr + c0 + 32, v2);
+          tmem_ld16_nowait(taddr + c0 + 48, v3);
           tmem_ld_wait();
         }
-        const float* bia = s_bias + c0 + 32 * grp;
-        const float* nwv = s_nw + c0 + 32 * grp;
+        uint8_t* srow = sblk + lane * 128;
         auto emit16 = [&](const uint32_t (&v)[16], int o) {
           uint32_t packed[8];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            float a = __uint_as_float(v[2 * jj]) + bia[o + 2 * jj];
-            float b = __uint_as_float(v[2 * jj + 1]) + bia[o + 2 * jj + 1];
+            float a = __uint_as_float(v[2 * jj]) + s_bias[c0 + o + 2 * jj];
+            float b = __uint_as_float(v[2 * jj + 1]) + s_bias[c0 + o + 2 * jj + 1];
             if (p.noise) {
-              a = fmaf(nwv[o + 2 * jj], nz, a);
-              b = fmaf(nwv[o + 2 * jj + 1], nz, b);
+              a = fmaf(s_nw[c0 + o + 2 * jj], nz, a);
+              b = fmaf(s_nw[c0 + o + 2 * jj + 1], nz, b);
             }
             if (p.act) { a = fmaxf(a, SG_LRELU_SLOPE * a); b = fmaxf(b, SG_LRELU_SLOPE * b); }
             __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
             packed[jj] = *reinterpret_cast<uint32_t*>(&h2);
           }
           if (!(p.dbg & 1)) st_global_256(dst + c0 + o, packed);
-          if (STATS) {
-            // staging row = 64 bytes (4 chunks of 16 B), chunk index XOR-ed with (row >> 1) & 3: the row-wise 16-byte
-            // stores of a quarter warp and the column-wise 4-byte loads below are both bank-conflict free
-            const int ch = o >> 3;
-            const int sw = (lane >> 1) & 3;
-            uint8_t* srow = sblk + lane * 64;
-            *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ sw) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ sw) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          if (STATS) {                                      // the ROUNDED values, as the consumer will read them
+            const int ch = o >> 3;                          // logical 16-byte chunk of this pixel row (8 channels each)
+            *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ (lane & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ (lane & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
           }
         };
         emit16(v0, 0);
         emit16(v1, 16);
+        emit16(v2, 32);
+        emit16(v3, 48);
         if (STATS) {
           __syncwarp();
-          // lane = (row half h, word w): sums channels 2w, 2w+1 over 16 of the warp's 32 pixel rows; the second half
-          // walks rows of the opposite parity so the two halves never meet in a bank
-          const int w = lane & 15, h = lane >> 4;
+          // lane l sums channels 2l, 2l+1 (one 32-bit word) over the warp's 32 pixel rows
+          const uint8_t* sb = sblk + ((lane & 3) << 2);
+          const int lch = lane >> 2;
           float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const int row = h * 16 + (r ^ h);
-            const uint32_t x = *reinterpret_cast<const uint32_t*>(sblk + row * 64 + ((((w >> 2) ^ ((row >> 1) & 3))) << 4) +
-                                                                  ((w & 3) << 2));
-            const float lo = __uint_as_float(x << 16), hi = __uint_as_float(x & 0xffff0000u);
+          for (int r = 0; r < 32; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sb + r * 128 + ((lch ^ (r & 7)) << 4));
+            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
             a0 += lo; a1 += hi;
             b0 = fmaf(lo, lo, b0); b1 = fmaf(hi, hi, b1);
           }
-          a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-          b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
           __syncwarp();                                     // the next chunk overwrites the staging block
           st_s[c][0] += a0; st_s[c][1] += a1;
           st_q[c][0] += b0; st_q[c][1] += b1;
@@ -325,10 +322,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (leader_cta) mbar_arrive(&bars->tmem_empty[acc]);
-        else mbar_arrive_remote(empty_remote + (uint32_t)(acc * 8));
+        if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
+        else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      acc_phase ^= 1;
     }
     if (STATS && cur_n >= 0) flush(cur_n);
   }
@@ -403,13 +400,22 @@ static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl, bool sta
   if (pl->num_spatial % 2 != 0) return false;
   pl->Q = pl->num_spatial / 2;
   pl->kchunks = Cin / BK;
-  pl->resident = resident_ok(Cin, pl->HB) ? 1 : 0;
-  pl->w_bytes = pl->resident ? 9 * pl->kchunks * pl->HB * BK * 2 : 0;
-  pl->stage_bytes = pl->resident ? A_BYTES : A_BYTES + 3 * pl->HB * BK * 2;
-  // 227 KB per CTA = static (bias / noise weights / reduction scratch 4 KB, + 16 KB statistics staging) + dynamic
-  const int budget = 232448 - (stats ? 20608 : 4224) - (int)sizeof(Barriers) - 1024 - 256;
-  int stages = (budget - pl->w_bytes) / pl->stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  // 227 KB per CTA = static (bias / noise weights / reduction scratch 6 KB, + 32 KB statistics staging) + dynamic
+  const int budget = 232448 - (stats ? 39040 : 6272) - (int)sizeof(Barriers) - 1024 - 256;
+  auto plan_for = [&](int resident, int* stage_bytes, int* w_bytes) {
+    *w_bytes = resident ? 9 * pl->kchunks * pl->HB * BK * 2 : 0;
+    *stage_bytes = resident ? A_BYTES : A_BYTES + 3 * pl->HB * BK * 2;
+    int st = (budget - *w_bytes) / *stage_bytes;
+    return st > MAX_STAGES ? MAX_STAGES : st;
+  };
+  int sb = 0, wb = 0;
+  int stages = resident_ok(Cin, pl->HB) ? plan_for(1, &sb, &wb) : 0;
+  pl->resident = 1;
+  if (stages < 3) {                                        // weights resident leave too few activation stages: stream them
+    stages = plan_for(0, &sb, &wb);
+    pl->resident = 0;
+  }
+  pl->stage_bytes = sb; pl->w_bytes = wb;
   if (stages < 2) return false;
   pl->stages = stages;
   int cols = 32;
@@ -433,7 +439,7 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
     err = cudaFuncSetAttribute(conv3x3_pair_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               232448 - (STATS ? 20608 : 4224));
+                               232448 - (STATS ? 39040 : 6272));
   });
   if (err != cudaSuccess) { sg_set_error("sg_conv3x3_pair: cannot raise the dynamic shared memory limit"); return (int)err; }
   conv3x3_pair_kernel<STATS><<<pl.grid, NUM_THREADS, pl.smem, st>>>(mx, mw, p);

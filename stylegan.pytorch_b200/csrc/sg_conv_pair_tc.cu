@@ -55,7 +55,7 @@ struct Params {
   int act;
   const float* noise;                             // [N,H,W] fp32 or null
   const float* noise_w;                           // [Cout]
-  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads, 4 = empty epilogue
+  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads, 4 = empty epilogue, 8 = no statistics pass
   float* part;                                    // [N][slots][2][Cout] fp32 or null; slots = 2*pairs
   __nv_bfloat16* y;
 };
@@ -291,7 +291,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             packed[jj] = *reinterpret_cast<uint32_t*>(&h2);
           }
           if (!(p.dbg & 1)) st_global_256(dst + c0 + o, packed);
-          if (STATS) {                                      // the ROUNDED values, as the consumer will read them
+          if (STATS && !(p.dbg & 8)) {                      // the ROUNDED values, as the consumer will read them
             const int ch = o >> 3;                          // logical 16-byte chunk of this pixel row (8 channels each)
             *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ (lane & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ (lane & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
@@ -301,7 +301,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         emit16(v1, 16);
         emit16(v2, 32);
         emit16(v3, 48);
-        if (STATS) {
+        if (STATS && !(p.dbg & 8)) {
           __syncwarp();
           // lane l sums channels 2l, 2l+1 (one 32-bit word) over the warp's 32 pixel rows
           const uint8_t* sb = sblk + ((lane & 3) << 2);

@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(256) channel_sum_vec_kernel(const T* __restric
         const long long p = pb + (long long)u * PR;
         if (p < p1) {
           v[u].load(x + (size_t)p * C + cv * V::N);
-          long long n = p / HW;
-          int hw = (int)(p - n * HW);
+          const unsigned n = (unsigned)p / (unsigned)HW;          // P < 2^31 (launcher): 32-bit division
+          const int hw = (int)((unsigned)p - n * (unsigned)HW);
 #pragma unroll
           for (int j = 0; j < CS_ROWS; ++j)
             w[u][j] = (j < J) ? wt[((size_t)n * J + j) * HW + hw] : ((ones && j == J) ? 1.f : 0.f);
@@ -923,6 +923,7 @@ SG_EXPORT int sg_channel_sum(const void* x, int dtype, const float* wt, int J, i
   int rows = J + (ones ? 1 : 0);
   SG_REQUIRE(rows >= 1 && rows <= CS_ROWS && J >= 0, "sg_channel_sum: rows must be 1..4");
   SG_REQUIRE(J == 0 || wt != nullptr, "sg_channel_sum: weights missing");
+  SG_REQUIRE(P < (1ll << 31), "sg_channel_sum: too many pixels");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_sg_fast_paths && dtype == SG_BF16 && J == 1 && ones && !accumulate) {
     // noise-weight + bias gradient: one per-pixel weight row plus the plain sum (same workspace layout and blocks)

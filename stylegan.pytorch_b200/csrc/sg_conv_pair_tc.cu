@@ -65,7 +65,8 @@ __device__ __forceinline__ int colsum_channel(int lane, int j) { return 2 * lane
 
 template <bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Params p) {
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_y, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem + (size_t)p.stages * p.stage_bytes;
@@ -86,7 +87,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   // both the row-wise 16-byte stores and the column-wise 4-byte loads are bank-conflict free).  Column sums through
   // shared memory cost ~64 wavefronts per warp and chunk; a shuffle butterfly (tried first: 248 SHFL per warp and
   // chunk) made the epilogue 3x slower than the MMAs it has to hide behind.
-  __shared__ __align__(16) uint8_t s_stage[STATS ? 8 * 4096 : 16];
+  __shared__ __align__(1024) uint8_t s_stage[STATS ? 8 * 4096 : 16];   // TMA-store source: 128B-swizzle atoms
   for (int i = threadIdx.x; i < p.BN; i += blockDim.x) {
     s_bias[i] = p.bias ? p.bias[n0 + i] * p.bias_mul : 0.f;
     s_nw[i] = (p.noise && p.noise_w) ? p.noise_w[n0 + i] : 0.f;
@@ -257,6 +258,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
       if (((q - q_begin) & 1) != team) continue;            // the other team's tile (accumulator buffer = team)
       const size_t pix = pixel_of(q);
+      const int rt = (2 * q + (int)rank) % p.tiles_per_image;
+      const int tile_w0 = (rt % p.tiles_w) * TW, tile_h0 = (rt / p.tiles_w) * TH;
       const float nz = nz_next;
       if (p.noise && q + 2 < q_end) nz_next = p.noise[pixel_of(q + 2)];
       mbar_wait(&bars->tmem_full[team], acc_phase);
@@ -290,19 +293,37 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
             packed[jj] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          if (!(p.dbg & 1)) st_global_256(dst + c0 + o, packed);
-          if (STATS && !(p.dbg & 8)) {                      // the ROUNDED values, as the consumer will read them
+          if (!STATS && !(p.dbg & 1)) st_global_256(dst + c0 + o, packed);
+          if (STATS) {                                      // the ROUNDED values, as the consumer will read them
             const int ch = o >> 3;                          // logical 16-byte chunk of this pixel row (8 channels each)
             *reinterpret_cast<uint4*>(srow + (((ch + 0) ^ (lane & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ (lane & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
           }
         };
+        if (STATS) {
+          // the previous TMA store out of this warp's staging block must have finished READING it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         emit16(v0, 0);
         emit16(v1, 16);
         emit16(v2, 32);
         emit16(v3, 48);
-        if (STATS && !(p.dbg & 8)) {
+        if (STATS) {
+          // The staged block IS the output: 32 pixels (two rows of the 8x16 tile) x 64 channels in the 128B-swizzle
+          // layout.  One TMA store per warp and chunk replaces 4 x st.global.v8 per thread, whose 32-byte pieces landed in
+          // 32 different 128-byte lines per instruction (512 LSU cycles per tile: the epilogue's largest single cost).
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
+          if (lane == 0 && !(p.dbg & 1)) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(sblk)), "r"(n0 + c0), "r"(tile_w0),
+                           "r"(tile_h0 + 2 * qd), "r"(n)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (STATS && !(p.dbg & 8)) {
           // lane l sums channels 2l, 2l+1 (one 32-bit word) over the warp's 32 pixel rows
           const uint8_t* sb = sblk + ((lane & 3) << 2);
           const int lch = lane >> 2;
@@ -328,6 +349,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       acc_phase ^= 1;
     }
     if (STATS && cur_n >= 0) flush(cur_n);
+    if (STATS && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
   }
 
   tc_fence_before();
@@ -434,7 +456,8 @@ static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl, bool sta
 }
 
 template <bool STATS>
-static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, const Plan& pl, cudaStream_t st) {
+static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const Params& p, const Plan& pl,
+                  cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
@@ -442,7 +465,7 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
                                232448 - (STATS ? 39040 : 6272));
   });
   if (err != cudaSuccess) { sg_set_error("sg_conv3x3_pair: cannot raise the dynamic shared memory limit"); return (int)err; }
-  conv3x3_pair_kernel<STATS><<<pl.grid, NUM_THREADS, pl.smem, st>>>(mx, mw, p);
+  conv3x3_pair_kernel<STATS><<<pl.grid, NUM_THREADS, pl.smem, st>>>(mx, mw, my, p);
   return sg_check_launch("sg_conv3x3_pair");
 }
 
@@ -494,7 +517,10 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
   }
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t st = (cudaStream_t)stream;
-  return part ? launch<true>(map_x, map_w, p, pl, st) : launch<false>(map_x, map_w, p, pl, st);
+  CUtensorMap map_y = map_x;                                // placeholder for the plain kernel (never dereferenced)
+  if (part)                                                 // TMA-store boxes: 64 channels x 16 pixels x 2 rows
+    SG_REQUIRE(encode_nhwc(&map_y, y, N, H, W, Cout, TW, 2), "sg_conv3x3_pair: cuTensorMapEncodeTiled(y) failed");
+  return part ? launch<true>(map_x, map_w, map_y, p, pl, st) : launch<false>(map_x, map_w, map_y, p, pl, st);
 }
 
 // part as written by sg_conv3x3_pair for the same (N, H, W, Cin, Cout); style [N, 2*Cout] or null; mr [N,Cout,2];

@@ -278,6 +278,16 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           tmem_ld16_nowait(taddr + c0 + 48, v3);
           tmem_ld_wait();
         }
+        if (c == nchunks - 1) {
+          // the accumulator is in registers: hand the TMEM buffer back NOW, so that the MMAs of the tile after next do
+          // not wait for this tile's arithmetic, stores and statistics
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
+            else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
+          }
+        }
         uint8_t* srow = sblk + lane * 128;
         auto emit16 = [&](const uint32_t (&v)[16], int o) {
           uint32_t packed[8];
@@ -340,11 +350,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           st_q[c][0] += b0; st_q[c][1] += b1;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
-        else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
+      if (p.dbg & 4) {                                      // (empty-epilogue probe: the loop above did not run)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
+          else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
+        }
       }
       acc_phase ^= 1;
     }

@@ -209,14 +209,16 @@ convud_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (nld > 2) tmem_ld16_nowait(taddr + c0 + 32, v2);
           if (nld > 3) tmem_ld16_nowait(taddr + c0 + 48, v3);
           tmem_ld_wait();
+          if (c0 + 64 >= p.BN) {                            // last chunk is in registers: release the TMEM buffer now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+          }
           emit16(v0, c0);
           if (nld > 1) emit16(v1, c0 + 16);
           if (nld > 2) emit16(v2, c0 + 32);
           if (nld > 3) emit16(v3, c0 + 48);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -393,16 +395,18 @@ convud_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           tmem_ld16_nowait(taddr + c0 + 32, v2);
           tmem_ld16_nowait(taddr + c0 + 48, v3);
           tmem_ld_wait();
+          if (c0 + 64 >= p.BN) {                            // last chunk is in registers: release the TMEM buffer now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader_cta) mbar_arrive(&bars->tmem_empty[acc]);
+              else mbar_arrive_remote(empty_remote + (uint32_t)(acc * 8));
+            }
+          }
           emit16(v0, c0);
           emit16(v1, c0 + 16);
           emit16(v2, c0 + 32);
           emit16(v3, c0 + 48);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (leader_cta) mbar_arrive(&bars->tmem_empty[acc]);
-          else mbar_arrive_remote(empty_remote + (uint32_t)(acc * 8));
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }

@@ -97,27 +97,35 @@ __global__ void __launch_bounds__(256) lingroup_fwd_kernel(const LinGroup* __res
 
 // ---- data gradient: gx_g[b, i] = scale_g * sum_o gy_g[b, o] W_g[o, i];  block = (group, 64 input columns) ----------------
 // gx is written with row stride ldx into the tensor x points at (for the StyleMod group: the gradient of dlatents[:, l]).
+// grid (G * I/64, OS) in clusters (1, OS): CTA y of a cluster walks its share of the group's 64-wide o chunks, then the OS
+// partial tiles are added in rank order through distributed shared memory (rank r finishes rows r, r + OS, ...): one
+// writer and one summation order per element, and the chain of dependent weight-load rounds is OS times shorter.
+constexpr int LGD_SPLIT = 8;
 __global__ void __launch_bounds__(256) lingroup_dgrad_kernel(const LinGroup* __restrict__ tab, int G, int B, int I,
                                                              int accumulate) {
   __shared__ float gs[LG_B][65];                       // gy chunk [b][o within chunk of 64]
+  __shared__ float red[LG_B][64];
   const int col_blocks = I / 64;
   const int g = blockIdx.x / col_blocks, cb = blockIdx.x % col_blocks;
+  const int OS = gridDim.y, z = blockIdx.y;
   const LinGroup t = tab[g];
   const int O = (int)t.O;
-  const int i = cb * 64 + (threadIdx.x & 63), bq = threadIdx.x >> 6;      // 4 batch quarters of 8 rows
+  const int il = threadIdx.x & 63, i = cb * 64 + il, bq = threadIdx.x >> 6;      // 4 batch quarters of 8 rows
   const float* Wp = reinterpret_cast<const float*>(t.W);
   const float* gyp = reinterpret_cast<const float*>(t.y);
+  const int chunks = (O + 63) / 64, per = (chunks + OS - 1) / OS;
+  const int o_begin = min(O, z * per * 64), o_end = min(O, (z + 1) * per * 64);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int oc = 0; oc < O; oc += 64) {
+  for (int oc = o_begin; oc < o_end; oc += 64) {
     __syncthreads();
     for (int e = threadIdx.x; e < LG_B * 64; e += blockDim.x) {
       const int b = e >> 6, o = e & 63;
-      gs[b][o] = (b < B && oc + o < O) ? gyp[(size_t)b * O + oc + o] : 0.f;
+      gs[b][o] = (b < B && oc + o < o_end) ? gyp[(size_t)b * O + oc + o] : 0.f;
     }
     __syncthreads();
-    const int on = min(64, O - oc);
+    const int on = min(64, o_end - oc);
     float wv[8];
     for (int o = 0; o < on; o += 8) {                  // 8 independent weight loads per thread in flight
 #pragma unroll
@@ -131,13 +139,24 @@ __global__ void __launch_bounds__(256) lingroup_dgrad_kernel(const LinGroup* __r
   const float scale = lo_f(t.scales);
   float* gx = reinterpret_cast<float*>(t.x);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int b = bq * 8 + j;
-    if (b < B) {
-      float* d = gx + (size_t)b * t.ldx + i;
-      *d = (accumulate ? *d : 0.f) + acc[j] * scale;
+  for (int j = 0; j < 8; ++j) red[bq * 8 + j][il] = acc[j];
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const uint32_t red_base = (uint32_t)__cvta_generic_to_shared(&red[0][0]);
+  for (int r = z + OS * bq; r < LG_B; r += OS * 4) {
+    float s = 0.f;
+    for (int k = 0; k < OS; ++k) {
+      uint32_t remote;
+      float v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(red_base + (uint32_t)(r * 64 + il) * 4u), "r"(k));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+      s += v;
+    }
+    if (r < B) {
+      float* d = gx + (size_t)r * t.ldx + i;
+      *d = (accumulate ? *d : 0.f) + s * scale;
     }
   }
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---- weight / bias gradient: gW_g[o, i] = scale_g * sum_b gy_g[b, o] x_g[b, i]; gb_g[o] = bmul_g * sum_b gy_g[b, o] --------
@@ -224,8 +243,16 @@ SG_EXPORT int sg_lingroup_fwd(const void* table, int G, int total_blocks, int B,
 
 SG_EXPORT int sg_lingroup_dgrad(const void* table, int G, int B, int I, int accumulate, void* stream) {
   SG_REQUIRE(sg_lingroup_supported(B, I), "sg_lingroup_dgrad: B must be <= 32 and I in {128, 256, 512}");
-  lingroup_dgrad_kernel<<<G * (I / 64), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const LinGroup*>(table), G, B, I,
-                                                                      accumulate);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G * (I / 64), LGD_SPLIT);
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = LGD_SPLIT; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lingroup_dgrad_kernel, reinterpret_cast<const LinGroup*>(table), G, B, I, accumulate);
+  if (e != cudaSuccess) { sg_set_error("sg_lingroup_dgrad: launch failed"); return (int)e; }
   return sg_check_launch("sg_lingroup_dgrad");
 }
 

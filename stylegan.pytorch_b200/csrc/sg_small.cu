@@ -81,27 +81,35 @@ __global__ void linear_finish_kernel(float* __restrict__ y, const float* __restr
   y[i] = act ? sg_lrelu(s) : s;
 }
 
-// gx[b][i] = scale * sum_o gy[b][o] * W[o][i].  grid (ceil(I/64), ceil(B/32)): a thread owns column i for 8 batch rows
-// and walks ALL of o (gy staged in 64-wide chunks), so every output element has one writer and one summation order:
-// no atomics, bitwise reproducible.  Eight independent weight loads per thread are in flight at a time.
+// gx[b][i] = scale * sum_o gy[b][o] * W[o][i].  grid (ceil(I/64), ceil(B/32), OS) in clusters (1, 1, OS): a thread owns
+// column i for 8 batch rows; CTA z of a cluster walks its share of the 64-wide o chunks (gy staged in shared memory,
+// eight independent weight loads in flight), then the OS partial tiles are added in rank order through distributed
+// shared memory -- rank r finishes rows r, r + OS, ... -- so every output element has one writer and one summation
+// order: no atomics, no workspace, bitwise reproducible.  (Walking all of o in one CTA is a chain of O/8 dependent
+// load rounds: 139 us for the 512 x 512 mapping layers; the cluster split cuts the chain by OS.)
 constexpr int LD_BB = 32;
+constexpr int LD_MAX_SPLIT = 8;
 __global__ void __launch_bounds__(256) linear_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ W,
                                                            float scale, float* __restrict__ gx, int B, int I, int O) {
   __shared__ float gs[LD_BB][65];
-  const int i = blockIdx.x * 64 + (threadIdx.x & 63), bq = threadIdx.x >> 6;
+  __shared__ float red[LD_BB][64];
+  const int OS = gridDim.z, z = blockIdx.z;
+  const int il = threadIdx.x & 63, i = blockIdx.x * 64 + il, bq = threadIdx.x >> 6;
   const int b0 = blockIdx.y * LD_BB;
   const int ic = i < I ? i : I - 1;
+  const int chunks = (O + 63) / 64, per = (chunks + OS - 1) / OS;
+  const int o_begin = min(O, z * per * 64), o_end = min(O, (z + 1) * per * 64);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int oc = 0; oc < O; oc += 64) {
+  for (int oc = o_begin; oc < o_end; oc += 64) {
     __syncthreads();
     for (int e = threadIdx.x; e < LD_BB * 64; e += blockDim.x) {
       const int b = e >> 6, o = e & 63;
-      gs[b][o] = (b0 + b < B && oc + o < O) ? gy[(size_t)(b0 + b) * O + oc + o] : 0.f;
+      gs[b][o] = (b0 + b < B && oc + o < o_end) ? gy[(size_t)(b0 + b) * O + oc + o] : 0.f;
     }
     __syncthreads();
-    const int on = min(64, O - oc);
+    const int on = min(64, o_end - oc);
     float wv[8];
     for (int o = 0; o < on; o += 8) {
 #pragma unroll
@@ -112,13 +120,33 @@ __global__ void __launch_bounds__(256) linear_dgrad_kernel(const float* __restri
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(gs[bq * 8 + j][o + u], wv[u], acc[j]);
     }
   }
-  if (i < I) {
+  if (OS == 1) {
+    if (i < I) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int b = b0 + bq * 8 + j;
-      if (b < B) gx[(size_t)b * I + i] = acc[j] * scale;
+      for (int j = 0; j < 8; ++j) {
+        const int b = b0 + bq * 8 + j;
+        if (b < B) gx[(size_t)b * I + i] = acc[j] * scale;
+      }
     }
+    return;
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[bq * 8 + j][il] = acc[j];
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const uint32_t red_base = (uint32_t)__cvta_generic_to_shared(&red[0][0]);
+  for (int r = z + OS * bq; r < LD_BB; r += OS * 4) {          // rows r == z (mod OS); the 4 thread quarters interleave
+    float s = 0.f;
+    for (int k = 0; k < OS; ++k) {
+      uint32_t remote;
+      float v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(red_base + (uint32_t)(r * 64 + il) * 4u), "r"(k));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+      s += v;
+    }
+    if (i < I && b0 + r < B) gx[(size_t)(b0 + r) * I + i] = s * scale;
+  }
+  // nobody may exit while a peer still reads its tile
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // gW[o][i] (+)= scale * sum_b gy[b][o] * x[b*ldx + i];   gb[o] (+)= bias_mul * sum_b gy[b][o]
@@ -383,8 +411,18 @@ SG_EXPORT int sg_linear_fwd(const float* x, long long ldx, const float* W, const
 
 SG_EXPORT int sg_linear_dgrad(const float* gy, const float* W, float scale, float* gx, int B, int I, int O,
                               void* stream) {
-  dim3 grid(sg_cdiv(I, 64), sg_cdiv(B, LD_BB));
-  linear_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, W, scale, gx, B, I, O);
+  int os = sg_cdiv(O, 64);
+  if (os > LD_MAX_SPLIT) os = LD_MAX_SPLIT;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(sg_cdiv(I, 64), sg_cdiv(B, LD_BB), os);
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = os;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, linear_dgrad_kernel, gy, W, scale, gx, B, I, O);
+  if (e != cudaSuccess) { sg_set_error("sg_linear_dgrad: launch failed"); return (int)e; }
   return sg_check_launch("sg_linear_dgrad");
 }
 

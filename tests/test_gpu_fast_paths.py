@@ -156,3 +156,37 @@ def test_linear_fast_equals_general_and_torch(B, I, Oo, act):
     assert rel(fast[:n], yr.flatten()) < 1e-5
     assert rel(fast[-(Oo * I + Oo):-Oo], grads[1].flatten()) < 1e-5
     assert rel(fast[-Oo:], grads[2]) < 1e-5
+
+
+# ---- weight preparation (csrc/sg_conv_generic.cu: wprep_fwd_kernel / wprep_bwd_kernel) ------------------------------
+@pytest.mark.parametrize("co,ci,KK,npt", [(64, 64, 9, 9), (48, 80, 9, 16), (33, 7, 9, 9), (512, 512, 9, 9), (40, 24, 16, 16),
+                                          (96, 32, 1, 1), (5, 130, 9, 16)])
+@pytest.mark.parametrize("transpose", [0, 1])
+def test_wprep_fwd_bwd_match_einsum(co, ci, KK, npt, transpose):
+    """E[pt][a][b] = scale * sum_j coef[pt][j] W[co][ci][j] and its adjoint over pixel-split partials, for full tiles,
+    ragged tiles (sizes that are not multiples of the 32 x 32 tile / 128-position block) and every tap count in use."""
+    from models._lib import lib, ptr, code
+    g = torch.Generator(device="cpu").manual_seed(co * 131 + ci * 7 + KK + npt + transpose)
+    W = torch.randn(co, ci, KK, generator=g).to(DEV)
+    coef = torch.randn(npt, KK, generator=g).to(DEV)
+    scale = 0.37
+    ref = torch.einsum("pj,oij->pio", coef.double(), W.double()) * scale          # [npt, ci, co]
+    if transpose:
+        ref = ref.transpose(1, 2).contiguous()
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 4e-3)):
+        E = torch.full(ref.shape, float("nan"), device=DEV, dtype=dt)
+        assert lib.sg_wprep_fwd(ptr(W), ptr(E), code(dt), co, ci, KK, npt, ptr(coef), scale, transpose, _s()) == 0
+        assert rel(E, ref) < tol
+    for S in (1, 3, 6):
+        part = torch.randn(S, *ref.shape, generator=g).to(DEV)                    # [S, npt, a, b]
+        p = part.double().sum(0)
+        if transpose:
+            p = p.transpose(1, 2)                                                 # -> [npt, ci, co]
+        want = torch.einsum("pj,pio->oij", coef.double(), p) * scale
+        dW = torch.full((co, ci, KK), float("nan"), device=DEV)
+        assert lib.sg_wprep_bwd(ptr(part), S, ptr(dW), co, ci, KK, npt, ptr(coef), scale, transpose, 0, _s()) == 0
+        assert rel(dW, want) < 1e-5
+        base = torch.randn(co, ci, KK, generator=g).to(DEV)
+        acc = base.clone()
+        assert lib.sg_wprep_bwd(ptr(part), S, ptr(acc), co, ci, KK, npt, ptr(coef), scale, transpose, 1, _s()) == 0
+        assert rel(acc, want + base.double()) < 1e-5

@@ -55,7 +55,7 @@ struct Params {
   int act;
   const float* noise;                             // [N,H,W] fp32 or null
   const float* noise_w;                           // [Cout]
-  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads, 4 = empty epilogue, 8 = no statistics pass
+  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads, 4 = empty epilogue, 8 = no statistics pass, 16 = no bias / noise terms
   float* part;                                    // [N][slots][2][Cout] fp32 or null; slots = 2*pairs
   __nv_bfloat16* y;
 };
@@ -240,6 +240,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       for (int c = 0; c < 4; ++c) { st_s[c][0] = st_s[c][1] = st_q[c][0] = st_q[c][1] = 0.f; }
     };
 
+    const bool has_bias = p.bias != nullptr && !(p.dbg & 16);
+    const bool has_noise = p.noise != nullptr && p.noise_w != nullptr && !(p.dbg & 16);
     auto pixel_of = [&](int q) -> size_t {                 // this thread's pixel in the CTA's tile of pair q
       int r = 2 * q + (int)rank;
       const int wt = r % p.tiles_w; r /= p.tiles_w;
@@ -293,9 +295,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           uint32_t packed[8];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            float a = __uint_as_float(v[2 * jj]) + s_bias[c0 + o + 2 * jj];
-            float b = __uint_as_float(v[2 * jj + 1]) + s_bias[c0 + o + 2 * jj + 1];
-            if (p.noise) {
+            float a = __uint_as_float(v[2 * jj]), b = __uint_as_float(v[2 * jj + 1]);
+            if (has_bias) {                                 // (data-gradient launches carry no bias: no shared-memory reads)
+              a += s_bias[c0 + o + 2 * jj];
+              b += s_bias[c0 + o + 2 * jj + 1];
+            }
+            if (has_noise) {
               a = fmaf(s_nw[c0 + o + 2 * jj], nz, a);
               b = fmaf(s_nw[c0 + o + 2 * jj + 1], nz, b);
             }

@@ -63,7 +63,7 @@ struct Params {
 // statistics layout: after the per-warp column sums lane l holds channels 2l and 2l+1 of the 64-channel chunk
 __device__ __forceinline__ int colsum_channel(int lane, int j) { return 2 * lane + j; }
 
-template <bool STATS>
+template <bool STATS, bool N64>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_y, Params p) {
@@ -209,6 +209,149 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const uint32_t empty_remote = mapa_u32(smem_u32(&bars->tmem_empty[0]), 0);
     const int slot = 2 * j + (int)rank;
     const int slots = 2 * p.pairs;
+    if constexpr (STATS && N64) {
+      // ---- BN = 64 with statistics: everything per-channel lives in registers ---------------------------------------
+      // The accumulator is read with the 16x256b TMEM shape: a thread gets, for 4 of the warp's 32 pixels, the SAME 16
+      // channels (8k + 2*(lane&3) + {0,1}, k = 0..7).  So bias and noise weight of its channels are 32 registers loaded
+      // once per kernel, and the InstanceNorm sums of its (pixels x channels) are 32 registers carried across ALL tiles
+      // of an image: no per-tile column-sum pass and no per-value shared-memory read at all (the 32x32b form -- one
+      // pixel, 64 channels per thread -- spent 2/3 of the epilogue's shared-memory wavefronts on broadcast reads of
+      // bias / noise weight and on the column sums; profiles/r02_summary.md).  The cross-lane reduction (8 pixel groups)
+      // happens once per image in flush64.
+      const int rg = lane >> 2, cq = lane & 3;
+      float bia[16], nwv[16], ssum[16], ssq[16];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = n0 + 8 * k + 2 * cq + e;
+          bia[2 * k + e] = (p.bias && !(p.dbg & 16)) ? p.bias[col] * p.bias_mul : 0.f;
+          nwv[2 * k + e] = (p.noise && p.noise_w && !(p.dbg & 16)) ? p.noise_w[col] : 0.f;
+          ssum[2 * k + e] = 0.f; ssq[2 * k + e] = 0.f;
+        }
+      uint32_t acc_phase = 0;
+      int cur_n = -1;
+      uint8_t* const sblk = s_stage + (team * 4 + qd) * 4096;   // this warp's 32 px x 64 ch bf16 block (TMA-store source)
+
+      auto flush64 = [&](int n) {
+        // 8 pixel groups (lane bits 2..4) -> lanes 0..3, fixed butterfly order; then the 8 warps through shared memory
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int d = 4; d < 32; d <<= 1) {
+            ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], d);
+            ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], d);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (rg == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              s_red[team * 4 + qd][0][8 * k + 2 * cq + e] = ssum[2 * k + e];
+              s_red[team * 4 + qd][1][8 * k + 2 * cq + e] = ssq[2 * k + e];
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int t = (warp - 2) * 32 + lane;
+        if (t < 128) {
+          const int which = t >> 6, ch = t & 63;
+          float sum = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) sum += s_red[w8][which][ch];
+          p.part[(((size_t)n * slots + slot) * 2 + which) * p.Cout + n0 + ch] = sum;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+      };
+
+      // noise of this thread's 4 pixels: tile rows 2qd + h (h = 0, 1), columns rg and rg + 8
+      auto noise_of = [&](int q, float (&nz)[2][2]) {
+        int r = 2 * q + (int)rank;
+        const int wt = r % p.tiles_w; r /= p.tiles_w;
+        const int ht = r % p.tiles_h;
+        const int n = r / p.tiles_h;
+        const float* src = p.noise + ((size_t)n * p.H + (ht * TH + 2 * qd)) * p.W + wt * TW + rg;
+        nz[0][0] = src[0]; nz[0][1] = src[8]; nz[1][0] = src[p.W]; nz[1][1] = src[p.W + 8];
+      };
+      const bool use_noise = p.noise != nullptr && p.noise_w != nullptr && !(p.dbg & 16);
+      float nz_next[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+      if (use_noise && q_begin + team < q_end) noise_of(q_begin + team, nz_next);
+      for (int q = q_begin; q < q_end; ++q) {
+        const int n = (2 * q + (int)rank) / p.tiles_per_image;
+        if (n != cur_n && cur_n >= 0) flush64(cur_n);          // both teams see every image boundary, in the same order
+        cur_n = n;
+        if (((q - q_begin) & 1) != team) continue;            // the other team's tile (accumulator buffer = team)
+        const int rt = (2 * q + (int)rank) % p.tiles_per_image;
+        const int tile_w0 = (rt % p.tiles_w) * TW, tile_h0 = (rt / p.tiles_w) * TH;
+        float nz[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { nz[h][0] = nz_next[h][0]; nz[h][1] = nz_next[h][1]; }
+        if (use_noise && q + 2 < q_end) noise_of(q + 2, nz_next);
+        mbar_wait(&bars->tmem_full[team], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(team * 64);
+        uint32_t v[2][32];
+        if (!(p.dbg & 6)) {
+          tmem_ld_16x256b_x8_nowait(taddr, v[0]);
+          tmem_ld_16x256b_x8_nowait(taddr + (16u << 16), v[1]);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[0][i] = 0u; v[1][i] = 0u; }
+        }
+        // the accumulator is in registers: hand the TMEM buffer back now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
+          else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
+        }
+        if (!(p.dbg & 4)) {
+          // the previous TMA store out of this warp's staging block must have finished READING it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {                  // pixel i = 16h + 8jp + rg of the warp's 32
+              const float z = nz[h][jp];
+              uint8_t* srow = sblk + (16 * h + 8 * jp + rg) * 128 + cq * 4;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float a = __uint_as_float(v[h][4 * k + 2 * jp]) + bia[2 * k];
+                float b = __uint_as_float(v[h][4 * k + 2 * jp + 1]) + bia[2 * k + 1];
+                a = fmaf(nwv[2 * k], z, a);
+                b = fmaf(nwv[2 * k + 1], z, b);
+                if (p.act) { a = fmaxf(a, SG_LRELU_SLOPE * a); b = fmaxf(b, SG_LRELU_SLOPE * b); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                const uint32_t w = *reinterpret_cast<uint32_t*>(&h2);
+                // 128B-swizzle atom: 16-byte chunk k of pixel row i sits at chunk position k ^ (i & 7) = k ^ rg
+                *reinterpret_cast<uint32_t*>(srow + ((k ^ rg) << 4)) = w;
+                if (!(p.dbg & 8)) {                           // the ROUNDED values, as the consumer will read them
+                  const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+                  ssum[2 * k] += lo; ssum[2 * k + 1] += hi;
+                  ssq[2 * k] = fmaf(lo, lo, ssq[2 * k]); ssq[2 * k + 1] = fmaf(hi, hi, ssq[2 * k + 1]);
+                }
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 1)) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(sblk)), "r"(n0), "r"(tile_w0),
+                           "r"(tile_h0 + 2 * qd), "r"(n)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        acc_phase ^= 1;
+      }
+      if (cur_n >= 0) flush64(cur_n);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    } else {
     uint32_t acc_phase = 0;
     // running statistics of the current image (this team's tiles): lane l holds channels 2l, 2l+1 of each 64-ch chunk
     float st_s[4][2], st_q[4][2];
@@ -367,6 +510,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     if (STATS && cur_n >= 0) flush(cur_n);
     if (STATS && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    }
   }
 
   tc_fence_before();
@@ -472,17 +616,17 @@ static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl, bool sta
   return true;
 }
 
-template <bool STATS>
+template <bool STATS, bool N64>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const Params& p, const Plan& pl,
                   cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(conv3x3_pair_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    err = cudaFuncSetAttribute(conv3x3_pair_kernel<STATS, N64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                232448 - (STATS ? 39040 : 6272));
   });
   if (err != cudaSuccess) { sg_set_error("sg_conv3x3_pair: cannot raise the dynamic shared memory limit"); return (int)err; }
-  conv3x3_pair_kernel<STATS><<<pl.grid, NUM_THREADS, pl.smem, st>>>(mx, mw, my, p);
+  conv3x3_pair_kernel<STATS, N64><<<pl.grid, NUM_THREADS, pl.smem, st>>>(mx, mw, my, p);
   return sg_check_launch("sg_conv3x3_pair");
 }
 
@@ -537,7 +681,9 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
   CUtensorMap map_y = map_x;                                // placeholder for the plain kernel (never dereferenced)
   if (part)                                                 // TMA-store boxes: 64 channels x 16 pixels x 2 rows
     SG_REQUIRE(encode_nhwc(&map_y, y, N, H, W, Cout, TW, 2), "sg_conv3x3_pair: cuTensorMapEncodeTiled(y) failed");
-  return part ? launch<true>(map_x, map_w, map_y, p, pl, st) : launch<false>(map_x, map_w, map_y, p, pl, st);
+  static const bool no64 = getenv("SG_PAIR_NO64") != nullptr;            // bench only: the generic statistics epilogue at BN = 64
+  if (part && pl.BN == 64 && !no64) return launch<true, true>(map_x, map_w, map_y, p, pl, st);
+  return part ? launch<true, false>(map_x, map_w, map_y, p, pl, st) : launch<false, false>(map_x, map_w, map_y, p, pl, st);
 }
 
 // part as written by sg_conv3x3_pair for the same (N, H, W, Cin, Cout); style [N, 2*Cout] or null; mr [N,Cout,2];

@@ -1,6 +1,6 @@
 """models/_host_facade.py: CPU-resident module + CPU tensors -> executed on a device replica, CPU results (the calling
 convention of the reference's generate_* scripts).  The control flow is checked on CPU with the device transfer stubbed;
-the real thing is a `gpu_next` test (not yet run on hardware, excluded from -m gpu)."""
+the end-to-end case is a `gpu` test."""
 import pytest
 import torch
 import torch.nn as nn

@@ -1,5 +1,4 @@
-"""GPU input pipeline (models/_input.py): host-side pieces on CPU; the kernel itself is `gpu_next` (not yet run on
-hardware, excluded from -m gpu)."""
+"""GPU input pipeline (models/_input.py): host-side pieces on CPU; the kernel itself in the `gpu` tests below."""
 import numpy as np
 import pytest
 import torch

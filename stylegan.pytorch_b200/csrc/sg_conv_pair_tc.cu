@@ -31,14 +31,20 @@ using namespace tcu;
 constexpr int TH = 8, TW = 16, BK = 64;
 constexpr int HALO_ROWS = (TH + 2) * TW;           // 160 smem rows of 128 B per kw-shift
 constexpr int A_BYTES = HALO_ROWS * BK * 2;        // 20480
-constexpr int NUM_THREADS = 320;                   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int MAX_MMA_WARPS = 2;
+constexpr int NUM_THREADS = 320 + 32 * (MAX_MMA_WARPS - 1);   // TMA warp, MMA warp, 8 epilogue warps, further MMA warps
 constexpr int MAX_STAGES = 8;
 
+// Accumulator buffers in TMEM: nacc = 512 / BN (8 at BN = 64).  With two, the MMAs of tile q+2 wait for the whole
+// full -> epilogue -> empty hand-over of tile q (a chain of mbarrier hops across the CTA pair, ~3000 cycles even with an
+// empty epilogue) on top of the ~1550 cycles of tile q+1's MMAs: (L + T)/2 per tile.  More buffers let the MMA warp run
+// ahead of the epilogue teams, which still take every other tile each.
+constexpr int MAX_ACC = 8;
 struct __align__(8) Barriers {
   uint64_t full[MAX_STAGES];      // leader's copy is used: expect_tx by the leader, complete_tx from both CTAs' TMA
   uint64_t empty[MAX_STAGES];     // each CTA's own copy, arrived by the leader's multicast tcgen05.commit
-  uint64_t tmem_full[2];          // each CTA's own copy (multicast commit)
-  uint64_t tmem_empty[2];         // leader copy: the 4 warps of the owning team of each CTA arrive (count 8)
+  uint64_t tmem_full[MAX_ACC];    // each CTA's own copy (multicast commit)
+  uint64_t tmem_empty[MAX_ACC];   // leader copy: the 4 warps of the owning team of each CTA arrive (count 8)
   uint64_t wfull;                 // leader's copy: resident weights of both CTAs have landed
   uint32_t tmem_base;
   uint32_t pad;
@@ -48,14 +54,14 @@ struct Params {
   int N, H, W, Cin, Cout, BN, HB;                 // BN = MMA N (both halves), HB = BN/2 = weight rows per CTA
   int tiles_h, tiles_w, tiles_n, num_spatial, tiles_per_image;
   int Q, pairs;                                   // tile pairs per N block, clusters per N block
-  int kchunks, stages, stage_bytes, tmem_cols;
+  int kchunks, stages, stage_bytes, tmem_cols, nacc, mma_warps;
   int resident, w_bytes;
   const float* bias;
   float bias_mul;
   int act;
   const float* noise;                             // [N,H,W] fp32 or null
   const float* noise_w;                           // [Cout]
-  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads, 4 = empty epilogue, 8 = no statistics pass, 16 = no bias / noise terms
+  int dbg;                                        // bench only (SG_PAIR_DBG): 1 = no global stores, 2 = no TMEM loads, 4 = empty epilogue, 8 = no statistics pass, 16 = no bias / noise terms, 32 = no activation TMA loads after the first tile
   float* part;                                    // [N][slots][2][Cout] fp32 or null; slots = 2*pairs
   __nv_bfloat16* y;
 };
@@ -95,7 +101,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 8); }    // one team of 4 epilogue warps x 2 CTAs
+    for (int a = 0; a < MAX_ACC; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 8); }    // one team of 4 epilogue warps x 2 CTAs
     mbar_init(&bars->wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&map_x);
@@ -138,6 +144,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
             uint8_t* sB = sA + A_BYTES;
+            if ((p.dbg & 32) && p.resident && q > q_begin) {  // probe: no activation loads after the first tile (stale operands)
+              if (leader_cta) mbar_arrive(&bars->full[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             if (leader_cta) mbar_expect_tx(&bars->full[stage], stage_tx);
             tma2_load_4d(sA, &map_x, &bars->full[stage], kc * BK, w0 + kw - 1, h0 - 1, n);
             if (!p.resident)
@@ -149,23 +160,34 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader_cta) {
+  } else if (warp == 1 || warp >= 10) {
+    // ===================== MMA issuers (leader CTA only) =====================
+    // The MMA stream is ISSUE-bound, not tensor-bound: one warp needs ~65 cycles per tcgen05.mma (descriptor arithmetic
+    // on the uniform datapath, R2UR moves, barrier waits) while the pair executes a 256x64x16 MMA in 43; issuing every MMA
+    // twice cost +7 % (profiles/r02_summary.md).  So p.mma_warps warps (1 and 10, 11, ..., different scheduler quadrants)
+    // issue the MMAs of alternate tiles, each into its own accumulator buffers; the shared-memory stages are consumed in
+    // ring order by whichever warp owns the tile, and every commit tracks the issuing thread's own MMAs.
+    const int mw = warp == 1 ? 0 : warp - 9;                // issuer index
+    if (leader_cta && mw < p.mma_warps) {
       const uint32_t idesc = make_idesc_bf16(256, p.BN);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t sW = smem_u32(smem_w);
+      const int per_tile = p.kchunks * 3;                    // stages per tile
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      auto skip_tiles = [&](int n) {                         // advance the ring position past n tiles of other issuers
+        stage += n * per_tile;
+        while (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+      };
+      skip_tiles(mw);
       if (p.resident) { mbar_wait(&bars->wfull, 0); tc_fence_after(); }
       const uint32_t b_kh_stride = p.resident ? (uint32_t)(3 * b_tap_bytes) : (uint32_t)b_tap_bytes;
-      for (int q = q_begin; q < q_end; ++q) {
-        mbar_wait_cluster(&bars->tmem_empty[acc], acc_phase ^ 1);
+      for (int ti = mw; ti < q_end - q_begin; ti += p.mma_warps) {
+        const int acc = ti % p.nacc;
+        mbar_wait_cluster(&bars->tmem_empty[acc], ((uint32_t)(ti / p.nacc) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
-        for (int it = 0; it < p.kchunks * 3; ++it) {
+        for (int it = 0; it < per_tile; ++it) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sA = smem_base + (uint32_t)(stage * p.stage_bytes);
@@ -192,7 +214,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         if (elect_one_sync()) umma2_commit(&bars->tmem_full[acc]);
         __syncwarp();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        skip_tiles(p.mma_warps - 1);
       }
     }
   } else {
@@ -229,7 +251,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           nwv[2 * k + e] = (p.noise && p.noise_w && !(p.dbg & 16)) ? p.noise_w[col] : 0.f;
           ssum[2 * k + e] = 0.f; ssq[2 * k + e] = 0.f;
         }
-      uint32_t acc_phase = 0;
       int cur_n = -1;
       uint8_t* const sblk = s_stage + (team * 4 + qd) * 4096;   // this warp's 32 px x 64 ch bf16 block (TMA-store source)
 
@@ -289,9 +310,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
         for (int h = 0; h < 2; ++h) { nz[h][0] = nz_next[h][0]; nz[h][1] = nz_next[h][1]; }
         if (use_noise && q + 2 < q_end) noise_of(q + 2, nz_next);
-        mbar_wait(&bars->tmem_full[team], acc_phase);
+        const int ti = q - q_begin, buf = ti % p.nacc;        // accumulator buffer of this tile; phase = its use count
+        mbar_wait(&bars->tmem_full[buf], (uint32_t)(ti / p.nacc) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(team * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * 64);
         uint32_t v[2][32];
         if (!(p.dbg & 6)) {
           tmem_ld_16x256b_x8_nowait(taddr, v[0]);
@@ -305,8 +327,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
-          else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
+          if (leader_cta) mbar_arrive(&bars->tmem_empty[buf]);
+          else mbar_arrive_remote(empty_remote + (uint32_t)(buf * 8));
         }
         if (!(p.dbg & 4)) {
           // the previous TMA store out of this warp's staging block must have finished READING it
@@ -347,12 +369,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        acc_phase ^= 1;
       }
       if (cur_n >= 0) flush64(cur_n);
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
     } else {
-    uint32_t acc_phase = 0;
     // running statistics of the current image (this team's tiles): lane l holds channels 2l, 2l+1 of each 64-ch chunk
     float st_s[4][2], st_q[4][2];
 #pragma unroll
@@ -407,10 +427,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int tile_w0 = (rt % p.tiles_w) * TW, tile_h0 = (rt / p.tiles_w) * TH;
       const float nz = nz_next;
       if (p.noise && q + 2 < q_end) nz_next = p.noise[pixel_of(q + 2)];
-      mbar_wait(&bars->tmem_full[team], acc_phase);
+      const int ti = q - q_begin, buf = ti % p.nacc;          // accumulator buffer of this tile; phase = its use count
+      mbar_wait(&bars->tmem_full[buf], (uint32_t)(ti / p.nacc) & 1u);
       tc_fence_after();
       __nv_bfloat16* dst = p.y + pix * p.Cout + n0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(team * p.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * p.BN);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= nchunks || (p.dbg & 4)) break;
@@ -429,8 +450,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
-            else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
+            if (leader_cta) mbar_arrive(&bars->tmem_empty[buf]);
+            else mbar_arrive_remote(empty_remote + (uint32_t)(buf * 8));
           }
         }
         uint8_t* srow = sblk + lane * 128;
@@ -502,11 +523,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (leader_cta) mbar_arrive(&bars->tmem_empty[team]);
-          else mbar_arrive_remote(empty_remote + (uint32_t)(team * 8));
+          if (leader_cta) mbar_arrive(&bars->tmem_empty[buf]);
+          else mbar_arrive_remote(empty_remote + (uint32_t)(buf * 8));
         }
       }
-      acc_phase ^= 1;
     }
     if (STATS && cur_n >= 0) flush(cur_n);
     if (STATS && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
@@ -569,7 +589,7 @@ static int pick_bn(int Cout) {
 static bool resident_ok(int Cin, int HB) { return 9 * (Cin / BK) * HB * BK * 2 <= 150 * 1024; }
 
 struct Plan {
-  int BN, HB, tiles_n, num_spatial, Q, pairs, kchunks, resident, w_bytes, stage_bytes, stages, tmem_cols, grid;
+  int BN, HB, tiles_n, num_spatial, Q, pairs, kchunks, resident, w_bytes, stage_bytes, stages, tmem_cols, nacc, grid;
   size_t smem;
 };
 
@@ -601,8 +621,15 @@ static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl, bool sta
   pl->stage_bytes = sb; pl->w_bytes = wb;
   if (stages < 2) return false;
   pl->stages = stages;
+  // all 512 TMEM columns (one CTA per SM): nacc = 512 / BN accumulator buffers (SG_PAIR_NACC=2: the first version)
+  static const int nacc_env = getenv("SG_PAIR_NACC") ? atoi(getenv("SG_PAIR_NACC")) : 0;
+  int nacc = 512 / BN;
+  if (nacc > MAX_ACC) nacc = MAX_ACC;
+  if (nacc_env >= 2 && nacc_env < nacc) nacc = nacc_env;
+  if (nacc < 2) return false;
+  pl->nacc = nacc;
   int cols = 32;
-  while (cols < 2 * BN) cols <<= 1;
+  while (cols < nacc * BN) cols <<= 1;
   pl->tmem_cols = cols;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -668,7 +695,14 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
   p.tiles_h = H / TH; p.tiles_w = W / TW; p.tiles_n = pl.tiles_n;
   p.num_spatial = pl.num_spatial; p.tiles_per_image = p.tiles_h * p.tiles_w;
   p.Q = pl.Q; p.pairs = pl.pairs;
-  p.kchunks = pl.kchunks; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols;
+  p.kchunks = pl.kchunks; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols; p.nacc = pl.nacc;
+  {
+    static const int mmaw = getenv("SG_PAIR_MMAW") ? atoi(getenv("SG_PAIR_MMAW")) : MAX_MMA_WARPS;   // bench only
+    p.mma_warps = mmaw < 1 ? 1 : (mmaw > MAX_MMA_WARPS ? MAX_MMA_WARPS : mmaw);
+    // an issuer that starts a tile ahead waits on the SECOND fill of a ring slot when the ring is shorter than the tiles in
+    // flight, and an mbarrier parity wait cannot tell 'two phases ahead' from 'done': one issuer then
+    if (pl.stages < p.mma_warps * 3 * pl.kchunks) p.mma_warps = 1;
+  }
   p.resident = pl.resident; p.w_bytes = pl.w_bytes;
   p.bias = bias; p.bias_mul = bias_mul; p.act = act;
   p.noise = noise; p.noise_w = noise_w; p.part = part;

@@ -16,7 +16,7 @@ namespace cg = cooperative_groups;
 using namespace tcu;
 
 constexpr int A_BYTES = 160 * 128;               // the product kernel's halo tile: 160 rows of 128 B
-constexpr int B_BYTES = 256 * 128;               // up to 256 rows of 128 B
+constexpr int B_BYTES = 9 * 128 * 128;           // nine taps of up to 128 rows of 128 B (mode 5)
 constexpr int STAGES = 4;
 
 struct __align__(8) Bars2 {
@@ -159,8 +159,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_rate_pai
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = a0 + (uint64_t)((kh * 2048 + k * 32) >> 4);
-          const uint64_t bd = b0 + (uint64_t)((k * 32) >> 4);
-          if (leader) umma_pair(tmem_base, ad, bd, idesc, (g | kh | k) ? 1u : 0u);
+          // mode 5: a different B tile for every tap (kh, kw = g % 3), HB = N/2 rows of 128 B each, as the convolution has
+          const uint32_t tap_off = c.mode == 5 ? (uint32_t)(((g % 3) * 3 + kh) * (c.N / 2) * 128) : 0u;
+          const uint64_t bd = b0 + (uint64_t)((tap_off + k * 32) >> 4);
+          // mode 6: alternate between two accumulators per group (as the convolution's tiles do)
+          const uint32_t td = tmem_base + ((c.mode == 6 && ((g / 3) & 1)) ? (uint32_t)c.N : 0u);
+          if (leader) umma_pair(td, ad, bd, idesc, (g | kh | k) ? 1u : 0u);
         }
       }
       if (leader) umma_commit_pair(&bars->scratch[stage]);
@@ -191,11 +195,11 @@ int main() {
   const size_t smem = STAGES * A_BYTES + B_BYTES + sizeof(Bars2) + 1024;
   CK(cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(mma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const char* names[] = {"SS M=128", "SS M=64", "TS (A in TMEM)", "TS + cp per MMA", "SS pair M=256"};
+  const char* names[] = {"SS M=128", "SS M=64", "TS (A in TMEM)", "TS + cp per MMA", "SS pair M=256", "pair, B per tap", "pair, 2 accum"};
   struct Row { int mode, M, N; };
   std::vector<Row> rows = {{0, 128, 64}, {0, 128, 128}, {0, 128, 256}, {1, 64, 64},  {1, 64, 128}, {1, 64, 192},
                            {1, 64, 256}, {2, 128, 64},  {2, 128, 128}, {2, 128, 256}, {3, 128, 64}, {3, 128, 128},
-                           {4, 256, 64}, {4, 256, 128}, {4, 256, 256}};
+                           {4, 256, 64}, {4, 256, 128}, {4, 256, 256}, {5, 256, 64}, {5, 256, 128}, {5, 256, 256}, {6, 256, 64}, {6, 256, 128}};
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   std::vector<long long> h(sms);
@@ -204,7 +208,7 @@ int main() {
   for (const Row& r : rows) {
     Cfg2 c{r.mode, r.M, r.N, 600};
     auto launch = [&]() {
-      if (r.mode == 4) mma_rate_pair_kernel<<<sms / 2 * 2, 128, smem>>>(c, cyc);
+      if (r.mode >= 4) mma_rate_pair_kernel<<<sms / 2 * 2, 128, smem>>>(c, cyc);
       else mma_rate2_kernel<<<sms, 128, smem>>>(c, cyc);
     };
     launch();
@@ -217,7 +221,7 @@ int main() {
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= 3;
     const double mmas = (double)c.groups * 12;
-    const int ctas = r.mode == 4 ? sms / 2 : sms;        // instructions are issued by one CTA per pair in mode 4
+    const int ctas = r.mode >= 4 ? sms / 2 : sms;        // instructions are issued by one CTA per pair in mode 4
     CK(cudaMemcpy(h.data(), cyc, ctas * sizeof(long long), cudaMemcpyDeviceToHost));
     double cs = 0;
     for (int i = 0; i < ctas; ++i) cs += h[i] / mmas;

@@ -28,12 +28,22 @@ namespace tc2 {
 
 using namespace tcu;
 
-constexpr int TH = 8, TW = 16, BK = 64;
-constexpr int HALO_ROWS = (TH + 2) * TW;           // 160 smem rows of 128 B per kw-shift
-constexpr int A_BYTES = HALO_ROWS * BK * 2;        // 20480
+// Tile = 16 rows x 8 pixels (M = 128: 8-pixel tile row r = rows 8r..8r+7 of the MMA).  ONE halo box of 18 x 10 pixels per
+// 64-channel chunk serves all nine taps: TMA writes it as 180 dense 128-byte rows (128B swizzle), tap (kh, kw) is the
+// descriptor start address + (kh*10 + kw)*128 with a stride of 1280 B between the 8-row groups.  The tensor core applies
+// the swizzle to the absolute shared-memory address, so start addresses and group strides that are not multiples of the
+// 1024-byte swizzle atom read correctly with base_offset = 0 (tools/umma_shift_probe.cu, profiles/r02_umma_shift_probe.txt).
+// The first version loaded three kw-shifted 10 x 16 boxes (60 KB per chunk instead of 23 KB) to keep every descriptor
+// 1024-byte aligned.
+constexpr int TH = 16, TW = 8, BK = 64;
+constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
+constexpr int A_BOX_BYTES = HALO_H * HALO_W * BK * 2;   // 23040
+constexpr int A_BYTES = (A_BOX_BYTES + 1023) / 1024 * 1024;   // 23552: ring slots stay 1024-byte aligned
+constexpr int A_SBO = HALO_W * BK * 2;             // 1280 B between consecutive tile rows in the box
 constexpr int MAX_MMA_WARPS = 2;
 constexpr int NUM_THREADS = 320 + 32 * (MAX_MMA_WARPS - 1);   // TMA warp, MMA warp, 8 epilogue warps, further MMA warps
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 8;                      // activation ring slots (one 64-channel chunk of one tile each)
+constexpr int MAX_BSTAGES = 4;                     // streamed-weight ring slots (three vertical taps of one (chunk, kw) each)
 
 // Accumulator buffers in TMEM: nacc = 512 / BN (8 at BN = 64).  With two, the MMAs of tile q+2 wait for the whole
 // full -> epilogue -> empty hand-over of tile q (a chain of mbarrier hops across the CTA pair, ~3000 cycles even with an
@@ -43,6 +53,8 @@ constexpr int MAX_ACC = 8;
 struct __align__(8) Barriers {
   uint64_t full[MAX_STAGES];      // leader's copy is used: expect_tx by the leader, complete_tx from both CTAs' TMA
   uint64_t empty[MAX_STAGES];     // each CTA's own copy, arrived by the leader's multicast tcgen05.commit
+  uint64_t bfull[MAX_BSTAGES];    // the same pair for the streamed-weight ring (unused when the weights are resident)
+  uint64_t bempty[MAX_BSTAGES];
   uint64_t tmem_full[MAX_ACC];    // each CTA's own copy (multicast commit)
   uint64_t tmem_empty[MAX_ACC];   // leader copy: the 4 warps of the owning team of each CTA arrive (count 8)
   uint64_t wfull;                 // leader's copy: resident weights of both CTAs have landed
@@ -54,7 +66,7 @@ struct Params {
   int N, H, W, Cin, Cout, BN, HB;                 // BN = MMA N (both halves), HB = BN/2 = weight rows per CTA
   int tiles_h, tiles_w, tiles_n, num_spatial, tiles_per_image;
   int Q, pairs;                                   // tile pairs per N block, clusters per N block
-  int kchunks, stages, stage_bytes, tmem_cols, nacc, mma_warps;
+  int kchunks, stages, stage_bytes, bstages, tmem_cols, nacc, mma_warps;   // stage_bytes = A_BYTES; bstages = 0 if resident
   int resident, w_bytes;
   const float* bias;
   float bias_mul;
@@ -101,6 +113,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < p.bstages; ++s) { mbar_init(&bars->bfull[s], 1); mbar_init(&bars->bempty[s], 1); }
     for (int a = 0; a < MAX_ACC; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 8); }    // one team of 4 epilogue warps x 2 CTAs
     mbar_init(&bars->wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -130,9 +143,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           for (int t = 0; t < 9; ++t)
             tma2_load_2d(smem_w + (size_t)(kc * 9 + t) * b_tap_bytes, &map_w, &bars->wfull, kc * BK, t * p.Cout + wrow0);
       }
-      const uint32_t stage_tx = (uint32_t)(2 * (p.resident ? A_BYTES : A_BYTES + 3 * b_tap_bytes));
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, bstage = 0;
+      uint32_t phase = 0, bphase = 0;
       for (int q = q_begin; q < q_end; ++q) {
         int r = 2 * q + (int)rank;
         int wt = r % p.tiles_w; r /= p.tiles_w;
@@ -140,22 +152,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         int n = r / p.tiles_h;
         const int h0 = ht * TH, w0 = wt * TW;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int kw = 0; kw < 3; ++kw) {
-            mbar_wait(&bars->empty[stage], phase ^ 1);
-            uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
-            uint8_t* sB = sA + A_BYTES;
-            if ((p.dbg & 32) && p.resident && q > q_begin) {  // probe: no activation loads after the first tile (stale operands)
-              if (leader_cta) mbar_arrive(&bars->full[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
-              continue;
-            }
-            if (leader_cta) mbar_expect_tx(&bars->full[stage], stage_tx);
-            tma2_load_4d(sA, &map_x, &bars->full[stage], kc * BK, w0 + kw - 1, h0 - 1, n);
-            if (!p.resident)
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          if ((p.dbg & 32) && q > q_begin) {                  // probe: no activation loads after the first tile (stale operands)
+            if (leader_cta) mbar_arrive(&bars->full[stage]);
+          } else {
+            if (leader_cta) mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * A_BOX_BYTES));
+            tma2_load_4d(smem + (size_t)stage * A_BYTES, &map_x, &bars->full[stage], kc * BK, w0 - 1, h0 - 1, n);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (!p.resident) {
+            for (int kw = 0; kw < 3; ++kw) {
+              mbar_wait(&bars->bempty[bstage], bphase ^ 1);
+              uint8_t* sB = smem_w + (size_t)bstage * (3 * b_tap_bytes);
+              if (leader_cta) mbar_expect_tx(&bars->bfull[bstage], (uint32_t)(2 * 3 * b_tap_bytes));
               for (int kh = 0; kh < 3; ++kh)
-                tma2_load_2d(sB + kh * b_tap_bytes, &map_w, &bars->full[stage], kc * BK,
-                             (kh * 3 + kw) * p.Cout + wrow0);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                tma2_load_2d(sB + kh * b_tap_bytes, &map_w, &bars->bfull[bstage], kc * BK, (kh * 3 + kw) * p.Cout + wrow0);
+              if (++bstage == p.bstages) { bstage = 0; bphase ^= 1; }
+            }
           }
         }
       }
@@ -172,43 +185,58 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const uint32_t idesc = make_idesc_bf16(256, p.BN);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t sW = smem_u32(smem_w);
-      const int per_tile = p.kchunks * 3;                    // stages per tile
-      int stage = 0;
-      uint32_t phase = 0;
-      auto skip_tiles = [&](int n) {                         // advance the ring position past n tiles of other issuers
+      const int per_tile = p.kchunks;                        // activation ring slots per tile (weight ring: 3 per chunk)
+      int stage = 0, bstage = 0;
+      uint32_t phase = 0, bphase = 0;
+      auto skip_tiles = [&](int n) {                         // advance the ring positions past n tiles of other issuers
         stage += n * per_tile;
         while (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+        if (!p.resident) {
+          bstage += n * per_tile * 3;
+          while (bstage >= p.bstages) { bstage -= p.bstages; bphase ^= 1; }
+        }
       };
       skip_tiles(mw);
       if (p.resident) { mbar_wait(&bars->wfull, 0); tc_fence_after(); }
-      const uint32_t b_kh_stride = p.resident ? (uint32_t)(3 * b_tap_bytes) : (uint32_t)b_tap_bytes;
+      const uint32_t bstep = (p.resident ? (uint32_t)(3 * b_tap_bytes) : (uint32_t)b_tap_bytes) >> 4;   // kh -> kh + 1
       for (int ti = mw; ti < q_end - q_begin; ti += p.mma_warps) {
         const int acc = ti % p.nacc;
         mbar_wait_cluster(&bars->tmem_empty[acc], ((uint32_t)(ti / p.nacc) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
-        for (int it = 0; it < per_tile; ++it) {
+        for (int kc = 0; kc < per_tile; ++kc) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_base + (uint32_t)(stage * p.stage_bytes);
-          const int kw = it % 3, kc = it / 3;
-          const uint32_t sB = p.resident ? (sW + (uint32_t)((kc * 9 + kw) * b_tap_bytes)) : (sA + A_BYTES);
-          const uint64_t a0 = make_desc_sw128(sA);
-          const uint64_t b0 = make_desc_sw128(sB);
+          const uint64_t a0 = make_desc_sw128_sbo(smem_base + (uint32_t)(stage * A_BYTES), (uint32_t)A_SBO);
           const uint32_t a_lo = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32);
-          const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
-          const uint32_t bstep = b_kh_stride >> 4;
-          const bool leader = elect_one_sync();
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t al = a_lo + (uint32_t)((kh * (TW * 128) + k * 32) >> 4);
-              const uint32_t bl = b_lo + kh * bstep + (uint32_t)((k * 32) >> 4);
-              if (leader) umma2_bf16_lohi(tmem_d, al, a_hi, bl, b_hi, idesc, (it | kh | k) ? 1u : 0u);
+          for (int kw = 0; kw < 3; ++kw) {
+            uint32_t sB;
+            if (p.resident) sB = sW + (uint32_t)((kc * 9 + kw) * b_tap_bytes);
+            else {
+              mbar_wait(&bars->bfull[bstage], bphase);
+              tc_fence_after();
+              sB = sW + (uint32_t)(bstage * 3 * b_tap_bytes);
             }
+            const uint64_t b0 = make_desc_sw128(sB);
+            const uint32_t b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
+            const bool leader = elect_one_sync();
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t al = a_lo + (uint32_t)(((kh * HALO_W + kw) * 128 + k * 32) >> 4);
+                const uint32_t bl = b_lo + kh * bstep + (uint32_t)((k * 32) >> 4);
+                if (leader) umma2_bf16_lohi(tmem_d, al, a_hi, bl, b_hi, idesc, (kc | kw | kh | k) ? 1u : 0u);
+              }
+            }
+            if (!p.resident) {
+              if (leader) umma2_commit(&bars->bempty[bstage]);
+              if (++bstage == p.bstages) { bstage = 0; bphase ^= 1; }
+            }
+            __syncwarp();
           }
-          if (leader) umma2_commit(&bars->empty[stage]);
+          if (elect_one_sync()) umma2_commit(&bars->empty[stage]);
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -287,14 +315,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
       };
 
-      // noise of this thread's 4 pixels: tile rows 2qd + h (h = 0, 1), columns rg and rg + 8
+      // noise of this thread's 4 pixels (i = 16h + 8jp + rg of the warp's 32): tile rows 4qd + 2h + jp, column rg
       auto noise_of = [&](int q, float (&nz)[2][2]) {
         int r = 2 * q + (int)rank;
         const int wt = r % p.tiles_w; r /= p.tiles_w;
         const int ht = r % p.tiles_h;
         const int n = r / p.tiles_h;
-        const float* src = p.noise + ((size_t)n * p.H + (ht * TH + 2 * qd)) * p.W + wt * TW + rg;
-        nz[0][0] = src[0]; nz[0][1] = src[8]; nz[1][0] = src[p.W]; nz[1][1] = src[p.W + 8];
+        const float* src = p.noise + ((size_t)n * p.H + (ht * TH + 4 * qd)) * p.W + wt * TW + rg;
+        nz[0][0] = src[0]; nz[0][1] = src[p.W]; nz[1][0] = src[2 * p.W]; nz[1][1] = src[3 * p.W];
       };
       const bool use_noise = p.noise != nullptr && p.noise_w != nullptr && !(p.dbg & 16);
       float nz_next[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -364,7 +392,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           if (lane == 0 && !(p.dbg & 1)) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                          ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(sblk)), "r"(n0), "r"(tile_w0),
-                           "r"(tile_h0 + 2 * qd), "r"(n)
+                           "r"(tile_h0 + 4 * qd), "r"(n)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -489,7 +517,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         emit16(v2, 32);
         emit16(v3, 48);
         if (STATS) {
-          // The staged block IS the output: 32 pixels (two rows of the 8x16 tile) x 64 channels in the 128B-swizzle
+          // The staged block IS the output: 32 pixels (four rows of the 16x8 tile) x 64 channels in the 128B-swizzle
           // layout.  One TMA store per warp and chunk replaces 4 x st.global.v8 per thread, whose 32-byte pieces landed in
           // 32 different 128-byte lines per instruction (512 LSU cycles per tile: the epilogue's largest single cost).
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -497,7 +525,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           if (lane == 0 && !(p.dbg & 1)) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                          ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(sblk)), "r"(n0 + c0), "r"(tile_w0),
-                           "r"(tile_h0 + 2 * qd), "r"(n)
+                           "r"(tile_h0 + 4 * qd), "r"(n)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -589,7 +617,7 @@ static int pick_bn(int Cout) {
 static bool resident_ok(int Cin, int HB) { return 9 * (Cin / BK) * HB * BK * 2 <= 150 * 1024; }
 
 struct Plan {
-  int BN, HB, tiles_n, num_spatial, Q, pairs, kchunks, resident, w_bytes, stage_bytes, stages, tmem_cols, nacc, grid;
+  int BN, HB, tiles_n, num_spatial, Q, pairs, kchunks, resident, w_bytes, stage_bytes, stages, bstages, tmem_cols, nacc, grid;
   size_t smem;
 };
 
@@ -605,22 +633,26 @@ static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl, bool sta
   pl->kchunks = Cin / BK;
   // 227 KB per CTA = static (bias / noise weights / reduction scratch 6 KB, + 32 KB statistics staging) + dynamic
   const int budget = 232448 - (stats ? 39040 : 6272) - (int)sizeof(Barriers) - 1024 - 256;
-  auto plan_for = [&](int resident, int* stage_bytes, int* w_bytes) {
-    *w_bytes = resident ? 9 * pl->kchunks * pl->HB * BK * 2 : 0;
-    *stage_bytes = resident ? A_BYTES : A_BYTES + 3 * pl->HB * BK * 2;
-    int st = (budget - *w_bytes) / *stage_bytes;
-    return st > MAX_STAGES ? MAX_STAGES : st;
-  };
-  int sb = 0, wb = 0;
-  int stages = resident_ok(Cin, pl->HB) ? plan_for(1, &sb, &wb) : 0;
-  pl->resident = 1;
-  if (stages < 3) {                                        // weights resident leave too few activation stages: stream them
-    stages = plan_for(0, &sb, &wb);
-    pl->resident = 0;
+  // resident weights + as many activation slots as fit; else two rings: activation slots and (chunk, kw) weight slots
+  const int b_slot = 3 * pl->HB * BK * 2;
+  pl->stage_bytes = A_BYTES;
+  pl->resident = 0; pl->bstages = 0;
+  if (resident_ok(Cin, pl->HB)) {
+    const int wb = 9 * pl->kchunks * pl->HB * BK * 2;
+    int st = (budget - wb) / A_BYTES;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st >= 2 && st >= (pl->kchunks < 3 ? pl->kchunks + 1 : 3)) { pl->resident = 1; pl->w_bytes = wb; pl->stages = st; }
   }
-  pl->stage_bytes = sb; pl->w_bytes = wb;
-  if (stages < 2) return false;
-  pl->stages = stages;
+  if (!pl->resident) {
+    int bst = 2, st = (budget - bst * b_slot) / A_BYTES;
+    while (bst < MAX_BSTAGES && (budget - (bst + 1) * b_slot) / A_BYTES >= 4) {   // deepen the weight ring while >= 4 activation slots remain
+      ++bst;
+      st = (budget - bst * b_slot) / A_BYTES;
+    }
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st < 2) return false;
+    pl->stages = st; pl->bstages = bst; pl->w_bytes = bst * b_slot;
+  }
   // all 512 TMEM columns (one CTA per SM): nacc = 512 / BN accumulator buffers (SG_PAIR_NACC=2: the first version)
   static const int nacc_env = getenv("SG_PAIR_NACC") ? atoi(getenv("SG_PAIR_NACC")) : 0;
   int nacc = 512 / BN;
@@ -639,7 +671,7 @@ static bool make_plan(int N, int H, int W, int Cin, int Cout, Plan* pl, bool sta
   if (pairs < 1) return false;
   pl->pairs = pairs;
   pl->grid = pairs * pl->tiles_n * 2;
-  pl->smem = (size_t)stages * pl->stage_bytes + pl->w_bytes + sizeof(Barriers) + 1024;
+  pl->smem = (size_t)pl->stages * pl->stage_bytes + pl->w_bytes + sizeof(Barriers) + 1024;
   return true;
 }
 
@@ -679,7 +711,7 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
   EncodeTiledFn enc = get_encode();
   SG_REQUIRE(enc != nullptr, "sg_conv3x3_pair: cuTensorMapEncodeTiled unavailable");
   CUtensorMap map_x, map_w;
-  SG_REQUIRE(encode_nhwc(&map_x, x, N, H, W, Cin, TW, TH + 2), "sg_conv3x3_pair: cuTensorMapEncodeTiled(x) failed");
+  SG_REQUIRE(encode_nhwc(&map_x, x, N, H, W, Cin, HALO_W, HALO_H), "sg_conv3x3_pair: cuTensorMapEncodeTiled(x) failed");
   {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)9 * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
@@ -695,13 +727,13 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
   p.tiles_h = H / TH; p.tiles_w = W / TW; p.tiles_n = pl.tiles_n;
   p.num_spatial = pl.num_spatial; p.tiles_per_image = p.tiles_h * p.tiles_w;
   p.Q = pl.Q; p.pairs = pl.pairs;
-  p.kchunks = pl.kchunks; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.tmem_cols = pl.tmem_cols; p.nacc = pl.nacc;
+  p.kchunks = pl.kchunks; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.bstages = pl.bstages; p.tmem_cols = pl.tmem_cols; p.nacc = pl.nacc;
   {
     static const int mmaw = getenv("SG_PAIR_MMAW") ? atoi(getenv("SG_PAIR_MMAW")) : MAX_MMA_WARPS;   // bench only
     p.mma_warps = mmaw < 1 ? 1 : (mmaw > MAX_MMA_WARPS ? MAX_MMA_WARPS : mmaw);
     // an issuer that starts a tile ahead waits on the SECOND fill of a ring slot when the ring is shorter than the tiles in
     // flight, and an mbarrier parity wait cannot tell 'two phases ahead' from 'done': one issuer then
-    if (pl.stages < p.mma_warps * 3 * pl.kchunks) p.mma_warps = 1;
+    if (pl.stages < p.mma_warps * pl.kchunks || (!pl.resident && pl.bstages < p.mma_warps * 3 * pl.kchunks)) p.mma_warps = 1;
   }
   p.resident = pl.resident; p.w_bytes = pl.w_bytes;
   p.bias = bias; p.bias_mul = bias_mul; p.act = act;
@@ -713,8 +745,8 @@ SG_EXPORT int sg_conv3x3_pair(const void* x, const void* Etc, void* y, const flo
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap map_y = map_x;                                // placeholder for the plain kernel (never dereferenced)
-  if (part)                                                 // TMA-store boxes: 64 channels x 16 pixels x 2 rows
-    SG_REQUIRE(encode_nhwc(&map_y, y, N, H, W, Cout, TW, 2), "sg_conv3x3_pair: cuTensorMapEncodeTiled(y) failed");
+  if (part)                                                 // TMA-store boxes: 64 channels x 8 pixels x 4 rows (one warp's 32 pixels)
+    SG_REQUIRE(encode_nhwc(&map_y, y, N, H, W, Cout, TW, 4), "sg_conv3x3_pair: cuTensorMapEncodeTiled(y) failed");
   static const bool no64 = getenv("SG_PAIR_NO64") != nullptr;            // bench only: the generic statistics epilogue at BN = 64
   if (part && pl.BN == 64 && !no64) return launch<true, true>(map_x, map_w, map_y, p, pl, st);
   return part ? launch<true, false>(map_x, map_w, map_y, p, pl, st) : launch<false, false>(map_x, map_w, map_y, p, pl, st);

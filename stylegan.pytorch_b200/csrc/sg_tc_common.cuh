@@ -66,6 +66,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                         // layout: SWIZZLE_128B
   return d;
 }
+// the same with an explicit stride between 8-row groups (any multiple of 16 B: the swizzle is a function of the absolute
+// shared-memory address, so neither the start address nor the stride has to be a multiple of the 1024-byte atom)
+__device__ __forceinline__ uint64_t make_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
 __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -18,8 +18,8 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-SHAPES = [(2, 16, 16, 64, 64), (1, 8, 32, 64, 128), (3, 32, 32, 128, 64), (2, 16, 16, 512, 512), (2, 64, 64, 64, 64),
-          (4, 32, 16, 256, 256), (2, 16, 32, 128, 128), (6, 8, 16, 64, 64), (2, 32, 32, 256, 128), (1, 128, 128, 64, 64)]
+SHAPES = [(2, 16, 16, 64, 64), (2, 16, 24, 64, 128), (3, 32, 32, 128, 64), (2, 16, 16, 512, 512), (2, 64, 64, 64, 64),
+          (4, 32, 16, 256, 256), (2, 16, 32, 128, 128), (6, 16, 8, 64, 64), (2, 32, 32, 256, 128), (1, 128, 128, 64, 64)]
 
 
 @pytest.mark.parametrize("N,H,W,ci,co", SHAPES)

@@ -112,7 +112,8 @@ int sg_epi_finalize_slots(const float* part, int slots, const float* style, floa
  * mode 1 DOWN x [N,2H,2W,Cin] -> y [N,H,W,Cout], 4x4 taps stride 2    (CustomLayers.py:156-180 downscale conv; dgrad of up)
  * E [16][Cout][Cin] bf16 from sg_wprep_fwd with the tables of models/_geom.py; fused bias + LeakyReLU. */
 int sg_convud_tc_supported(int mode, int N, int H, int W, int Cin, int Cout);
-/* sg_convud_tc runs its CTA-pair (cta_group::2) kernel where the shape allows; 0 switches that off (A/B tests) */
+/* kernel choice of sg_convud_tc (A/B tests): 2 (default) the halo-box CTA-pair kernel of csrc/sg_convud2_tc.cu where the
+ * shape allows, 1 the first CTA-pair kernel, 0 the single-CTA kernel; < 0 queries.  Returns the previous value. */
 int sg_pair_updown(int enable);
 int sg_convud_tc(int mode, const void* x, const void* E, void* y, const float* bias, float bias_mul, int act, int N,
                  int H, int W, int Cin, int Cout, void* stream);

@@ -16,7 +16,11 @@
 #include "../../include/sgb200.h"
 #include "sg_tc_common.cuh"
 
-int g_sg_pair_updown = 1;      // sg_fast_paths-style switch for A/B tests (sg_pair_updown)
+int g_sg_pair_updown = 2;      // sg_fast_paths-style switch for A/B tests (sg_pair_updown): 0 single CTA, 1 first pair kernel, 2 halo-box pair kernel
+
+int sg_convud_halo_supported(int mode, int N, int H, int W, int Cin, int Cout);      // csrc/sg_convud2_tc.cu
+int sg_convud_halo(int mode, const void* x, const void* E, void* y, const float* bias, float bias_mul, int act, int N, int H,
+                   int W, int Cin, int Cout, void* stream);
 
 namespace ud {
 
@@ -468,6 +472,8 @@ SG_EXPORT int sg_convud_tc(int mode, const void* x, const void* E, void* y, cons
                            int N, int H, int W, int Cin, int Cout, void* stream) {
   using namespace ud;
   SG_REQUIRE(sg_convud_tc_supported(mode, N, H, W, Cin, Cout), "sg_convud_tc: shape not supported");
+  if (g_sg_pair_updown >= 2 && sg_convud_halo_supported(mode, N, H, W, Cin, Cout))
+    return sg_convud_halo(mode, x, E, y, bias, bias_mul, act, N, H, W, Cin, Cout, stream);
   EncodeTiledFn enc = get_encode();
   SG_REQUIRE(enc != nullptr, "sg_convud_tc: cuTensorMapEncodeTiled unavailable");
   const bool pair = g_sg_pair_updown && pair_ok(N, H, W, Cin, Cout);
@@ -536,9 +542,10 @@ SG_EXPORT int sg_convud_tc(int mode, const void* x, const void* E, void* y, cons
   return sg_check_launch("sg_convud_tc");
 }
 
-// 1 (default): the CTA-pair kernel where the shape allows; 0: single-CTA kernel only; <0: query.  Returns the old value.
+// 2 (default): the halo-box CTA-pair kernel (csrc/sg_convud2_tc.cu) where the shape allows, else as 1; 1: the first
+// CTA-pair kernel where the shape allows; 0: single-CTA kernel only; <0: query.  Returns the old value.
 SG_EXPORT int sg_pair_updown(int enable) {
   int old = g_sg_pair_updown;
-  if (enable >= 0) g_sg_pair_updown = enable ? 1 : 0;
+  if (enable >= 0) g_sg_pair_updown = enable > 2 ? 2 : enable;
   return old;
 }

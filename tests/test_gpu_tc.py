@@ -126,9 +126,9 @@ def test_up_down_layers_on_tensor_cores(kind, ci, co, hw):
 @pytest.mark.parametrize("direction", ["fwd", "dgrad"])
 @pytest.mark.parametrize("N,lo,ci,co", [(2, 16, 64, 64), (1, 32, 128, 64), (2, 16, 256, 128), (3, 64, 64, 128),
                                         (2, 16, 256, 256), (1, 8, 512, 512)])
-@pytest.mark.parametrize("pair", [1, 0])
+@pytest.mark.parametrize("pair", [2, 1, 0])
 def test_fused_updown_kernel_matches_oracle(kind, direction, N, lo, ci, co, pair):
-    """sg_convud_tc (tap-merged 4-phase 2x2 / 4x4-stride-2 tcgen05 kernels; CTA-pair and single-CTA forms) vs torch on
+    """sg_convud_tc (tap-merged 4-phase 2x2 / 4x4-stride-2 tcgen05 kernels; halo-box pair, first pair and single-CTA forms) vs torch on
     CPU, both directions."""
     import test_gpu_ops as T
     from models import _ops, _tc

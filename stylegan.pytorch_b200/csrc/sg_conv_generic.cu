@@ -257,9 +257,25 @@ __global__ void __launch_bounds__(256) wprep_fwd_kernel(const float* __restrict_
   const int tiles_ci = (Cin + WP_T - 1) / WP_T;
   const int co0 = (blockIdx.x / tiles_ci) * WP_T, ci0 = (blockIdx.x % tiles_ci) * WP_T;
   const int nci = min(WP_T, Cin - ci0), nco = min(WP_T, Cout - co0);
-  for (int i = threadIdx.x; i < nco * nci * KK; i += blockDim.x) {
-    const int c = i / (nci * KK), r = i % (nci * KK);
-    s_w[c * row + r] = W[((size_t)(co0 + c) * Cin + ci0) * KK + r] * scale;
+  {
+    // 8 independent loads in flight per thread (one load per loop trip left every trip waiting for its own DRAM round
+    // trip: 20-40 us for ANY weight size)
+    const int run = nci * KK, total = nco * run;
+    constexpr int U = 8;
+    for (int i0 = threadIdx.x; i0 < total; i0 += U * blockDim.x) {
+      float v[U];
+      int dsti[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const int c = i / run, r = i - c * run;
+        dsti[u] = c * row + r;
+        v[u] = i < total ? W[((size_t)(co0 + c) * Cin + ci0) * KK + r] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + u * (int)blockDim.x < total) s_w[dsti[u]] = v[u] * scale;
+    }
   }
   __syncthreads();
   const int A = transpose ? Cout : Cin, B = transpose ? Cin : Cout;
@@ -275,6 +291,7 @@ __global__ void __launch_bounds__(256) wprep_fwd_kernel(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 16; ++j) wv[j] = j < KK ? w[j] : 0.f;
     T* dst = E + (size_t)(a0 + al) * B + (b0 + bl);
+#pragma unroll 4
     for (int pt = 0; pt < npt; ++pt) {
       const float* cf = s_coef + pt * KK;
       float acc = 0.f;
@@ -311,18 +328,14 @@ wprep_bwd_kernel(const float* __restrict__ partial, int nsplit, float* __restric
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (vec && pos + 3 < total) {
       const float* p = partial + (size_t)pt * plane + (size_t)pos;
-      int sp = 0;
-      for (; sp + 4 <= nsplit; sp += 4) {
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < nsplit; sp += 4) {           // four independent (predicated) loads in flight
         const float4 v0 = *reinterpret_cast<const float4*>(p + (size_t)sp * split_stride);
-        const float4 v1 = *reinterpret_cast<const float4*>(p + (size_t)(sp + 1) * split_stride);
-        const float4 v2 = *reinterpret_cast<const float4*>(p + (size_t)(sp + 2) * split_stride);
-        const float4 v3 = *reinterpret_cast<const float4*>(p + (size_t)(sp + 3) * split_stride);
+        const float4 v1 = sp + 1 < nsplit ? *reinterpret_cast<const float4*>(p + (size_t)(sp + 1) * split_stride) : zero4;
+        const float4 v2 = sp + 2 < nsplit ? *reinterpret_cast<const float4*>(p + (size_t)(sp + 2) * split_stride) : zero4;
+        const float4 v3 = sp + 3 < nsplit ? *reinterpret_cast<const float4*>(p + (size_t)(sp + 3) * split_stride) : zero4;
         acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
         acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
-      }
-      for (; sp < nsplit; ++sp) {
-        const float4 v = *reinterpret_cast<const float4*>(p + (size_t)sp * split_stride);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     } else {
       float* av = &acc.x;
@@ -447,7 +460,6 @@ SG_EXPORT int sg_wprep_fwd(const float* W, void* E, int dtype, int Cout, int Cin
                            float scale, int transpose, void* stream) {
   SG_REQUIRE(KK >= 1 && KK <= 16 && npt >= 1, "sg_wprep_fwd: bad sizes");
   SG_REQUIRE(npt <= 64, "sg_wprep_fwd: too many effective taps");
-  long long total = (long long)Cout * Cin;
   cudaStream_t st = (cudaStream_t)stream;
   SG_DISPATCH(dtype, {
     const int tiles = sg_cdiv(Cout, WP_T) * sg_cdiv(Cin, WP_T);

@@ -560,9 +560,21 @@ def main():
                                    "per-image cost of this path does not depend on the batch), oracle port on the "
                                    "host CPU, all %d threads" % (R, R, cb, threads),
                                    "sec_per_step": [round(x, 2) for x in t]}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: the captured CUDA graphs hold NCCL kernels, and destroy_process_group() with
+        # them alive did not return on a 2-GPU box (the JSON line was out, torchrun waited for the ranks until its timeout).
+        # A barrier keeps the ranks together until rank 0 has printed; a watchdog bounds even that.
+        import threading
+        sys.stdout.flush(); sys.stderr.flush()
+        threading.Timer(60.0, lambda: os._exit(0)).start()
+        try:
+            torch.cuda.synchronize()
+            dist.barrier()
+        except Exception:
+            pass
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

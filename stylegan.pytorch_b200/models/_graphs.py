@@ -131,9 +131,21 @@ class StepGraphs:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         _ops._capture[0] = cap
+        # host-side state a failed capture must give back (the caller then runs the same step eagerly)
+        import random
+        host_state = (random.getstate(), torch.random.get_rng_state())
         try:
-            with torch.cuda.graph(g, pool=self.pool):
+            # thread_local: CUDA calls of OTHER threads stay legal during the capture -- with torch.distributed the NCCL
+            # watchdog thread queries events of earlier collectives, which invalidates a capture in the default global mode
+            # (seen with world size 2: cudaErrorStreamCaptureInvalidated)
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
                 e.loss = body(e.z, e.img, depth, alpha, None)
+        except BaseException:
+            random.setstate(host_state[0])
+            torch.random.set_rng_state(host_state[1])
+            _Noise.offset = off0
+            count_launch(l0 - launches())
+            raise
         finally:
             _ops._capture[0] = None
         if self.pool is None:

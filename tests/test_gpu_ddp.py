@@ -85,8 +85,16 @@ def _worker(rank, world, port, q):
         same = all(torch.equal(all_d[0], all_d[r]) for r in range(1, world))
         finite = all(x == x and abs(x) < 1e4 for pair in losses for x in pair)
         q.put((rank, err, differ, same, finite, captured))
-    finally:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down while captured graphs hold NCCL kernels (destroy_process_group did not return
+        # in that state on a 2-GPU box); the result is flushed to the parent first
+        q.close(); q.join_thread()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
@@ -98,9 +106,20 @@ def test_nccl_data_parallel_world2():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
+    import queue
+    import time
+    res, t0 = [], time.time()
+    while len(res) < world:                           # fail fast when a worker dies instead of waiting for its result
+        try:
+            res.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            assert not dead, "a worker exited with %s (traceback above)" % dead
+            assert time.time() - t0 < 300, "workers did not finish in 300 s"
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
+        if p.exitcode is None:
+            p.kill()
         assert p.exitcode == 0
     for rank, err, differ, same, finite, captured in res:
         assert err < 1e-5, (rank, err)                # NCCL sum * 1/world == mean of the ranks' gradients

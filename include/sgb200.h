@@ -163,6 +163,11 @@ int sg_axpby(const void* x, const void* y, void* out, float a, float b, long lon
 int sg_axpby_dev(const void* x, const void* y, void* out, const float* ab, long long n, int dtype, void* stream);
 /* LeakyReLU(0.2) backward from the activation output (GAN.py:68,151,347). */
 int sg_lrelu_bwd(const void* g, const void* ref, void* gx, long long n, int dtype, void* stream);
+/* the same plus the bias gradient of the fused conv + bias + LeakyReLU it belongs to (CustomLayers.py:77-80 add + the
+ * LeakyReLU of Blocks.py): gx over NHWC [P][C], gb[c] = scale * sum_p gx[p][c]; ws = sg_channel_sum_blocks(P) * C floats */
+int sg_lrelu_bwd_bias_supported(int dtype, long long P, int C);
+int sg_lrelu_bwd_bias(const void* g, const void* ref, void* gx, int dtype, long long P, int C, float* ws, float* gb,
+                      float scale, void* stream);
 int sg_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, void* stream);
 /* out[j][c] = scale * sum_p wt_j(p) * x[p][c]; wt [N][J][HW] float32, optional all-ones last row.  Bias, noise-weight,
  * from_rgb and to_rgb weight gradients.  part_ws: sg_channel_sum_blocks(P) * rows * C floats. */

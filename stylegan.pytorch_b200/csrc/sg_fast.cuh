@@ -11,6 +11,8 @@ int sgf_rgb_in3(const float* img, const float* W, const float* bias, float scale
 int sgf_rgb_out3(const void* x, const float* W, const float* bias, float scale, float bias_mul, float alpha, float beta,
                  float* out, int N, int h, int w, int C, int up, void* stream);
 int sgf_channel_sum_blocks(long long P);
+int sgf_channel_sum_w3(const void* x, const float* wt, int ones, long long P, int HW, int C, float* ws, float* out,
+                       float scale, void* stream);
 int sgf_channel_sum_w1(const void* x, const float* wt, long long P, int C, float* ws, float* out, float scale,
                        void* stream);
 int sgf_linear_fwd(const float* x, long long ldx, const float* W, const float* bias, float scale, float bias_mul, int act,

@@ -68,16 +68,42 @@ __global__ void adam_multi_kernel(const SgTensorEntry* __restrict__ tab, int T, 
   }
   long long i0 = (long long)(blockIdx.x - en.chunk0) * CHUNK;
   long long i1 = i0 + CHUNK < en.n ? i0 + CHUNK : en.n;
-  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    float gv = g[i] * gs;
-    float mv = beta1 * m[i] + (1.f - beta1) * gv;
-    float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
-    m[i] = mv;
-    v[i] = vv;
-    float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
-    float pv = p[i] - step_size * (mv / denom);
-    p[i] = pv;
-    if (ema) ema[i] = ema_beta * ema[i] + (1.f - ema_beta) * pv;
+  auto update = [&](float gvr, float& mr, float& vr, float& pr, float& er) {
+    const float gv = gvr * gs;
+    mr = beta1 * mr + (1.f - beta1) * gv;
+    vr = beta2 * vr + (1.f - beta2) * gv * gv;
+    const float denom = sqrtf(vr) * inv_sqrt_bc2 + eps;
+    pr = pr - step_size * (mr / denom);
+    er = ema_beta * er + (1.f - ema_beta) * pr;
+  };
+  // 16-byte path: chunk starts are multiples of 2048 elements, so alignment is that of the tensors' base pointers
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) & 15) == 0;
+  long long iv = i0;
+  if (vec) {
+    const long long n4 = (i1 - i0) / 4;
+    for (long long q = threadIdx.x; q < n4; q += blockDim.x) {
+      const long long i = i0 + 4 * q;
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float4 m4 = *reinterpret_cast<const float4*>(m + i);
+      float4 v4 = *reinterpret_cast<const float4*>(v + i);
+      float4 p4 = *reinterpret_cast<const float4*>(p + i);
+      float4 e4 = ema ? *reinterpret_cast<const float4*>(ema + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      update(g4.x, m4.x, v4.x, p4.x, e4.x);
+      update(g4.y, m4.y, v4.y, p4.y, e4.y);
+      update(g4.z, m4.z, v4.z, p4.z, e4.z);
+      update(g4.w, m4.w, v4.w, p4.w, e4.w);
+      *reinterpret_cast<float4*>(m + i) = m4;
+      *reinterpret_cast<float4*>(v + i) = v4;
+      *reinterpret_cast<float4*>(p + i) = p4;
+      if (ema) *reinterpret_cast<float4*>(ema + i) = e4;
+    }
+    iv = i0 + 4 * n4;
+  }
+  for (long long i = iv + threadIdx.x; i < i1; i += blockDim.x) {
+    float mr = m[i], vr = v[i], pr = p[i], er = ema ? ema[i] : 0.f;
+    update(g[i], mr, vr, pr, er);
+    m[i] = mr; v[i] = vr; p[i] = pr;
+    if (ema) ema[i] = er;
   }
 }
 

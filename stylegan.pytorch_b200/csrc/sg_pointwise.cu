@@ -157,6 +157,63 @@ __global__ void lrelu_bwd_kernel(const T* __restrict__ g, const T* __restrict__ 
     gx[i] = sg_from_f<T>(sg_to_f(ref[i]) > 0.f ? sg_to_f(g[i]) : SG_LRELU_SLOPE * sg_to_f(g[i]));
 }
 
+// gx = g * lrelu'(ref) AND part[blk][c] = sum over the block's pixels of the (rounded) gx: the backward of a fused
+// conv + bias + LeakyReLU needs both, and the bias gradient as a second pass re-read all of gx (channel_sum_ones_kernel).
+// Work split and partial layout of channel_sum_ones_kernel (a thread owns one 16-byte channel vector, strides over pixels).
+template <class T>
+__global__ void __launch_bounds__(256) lrelu_bwd_bias_kernel(const T* __restrict__ g, const T* __restrict__ ref,
+                                                             T* __restrict__ gx, long long P, int C,
+                                                             float* __restrict__ part, int pix_per_blk) {
+  using V = SgVec<T>;
+  extern __shared__ float sm[];                 // [PR][C]
+  const int CV = C / V::N;
+  const int PR = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, pr = threadIdx.x / CV;
+  const long long p0 = (long long)blockIdx.x * pix_per_blk;
+  long long p1 = p0 + pix_per_blk;
+  if (p1 > P) p1 = P;
+  float acc[V::N];
+#pragma unroll
+  for (int k = 0; k < V::N; ++k) acc[k] = 0.f;
+  if (pr < PR) {
+    constexpr int U = 4;                          // pixels in flight per thread (two loads each)
+    const size_t step = (size_t)PR * C;
+    long long pb = p0 + pr;
+    size_t off = (size_t)pb * C + cv * V::N;
+    for (; pb + (long long)(U - 1) * PR < p1; pb += (long long)U * PR, off += U * step) {
+      V vg[U], vr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { vg[u].load(g + off + u * step); vr[u].load(ref + off + u * step); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        V vo;
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) vo.set(k, vr[u].get(k) > 0.f ? vg[u].get(k) : SG_LRELU_SLOPE * vg[u].get(k));
+        vo.store(gx + off + u * step);
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) acc[k] += vo.get(k);
+      }
+    }
+    for (; pb < p1; pb += PR, off += step) {
+      V vg, vr, vo;
+      vg.load(g + off); vr.load(ref + off);
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) vo.set(k, vr.get(k) > 0.f ? vg.get(k) : SG_LRELU_SLOPE * vg.get(k));
+      vo.store(gx + off);
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) acc[k] += vo.get(k);
+    }
+#pragma unroll
+    for (int k = 0; k < V::N; ++k) sm[(size_t)pr * C + cv * V::N + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < PR; ++r) t += sm[(size_t)r * C + c];
+    part[(size_t)blockIdx.x * C + c] = t;
+  }
+}
+
 template <class TI, class TO>
 __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -896,6 +953,32 @@ SG_EXPORT int sg_lrelu_bwd(const void* g, const void* ref, void* gx, long long n
   return sg_check_launch("sg_lrelu_bwd");
 }
 
+// gx = g * lrelu'(ref) over [P][C] (NHWC) and gb[c] = scale * sum_p gx[p][c] in the same pass (two-stage, deterministic).
+// ws: sg_channel_sum_blocks(P) * C floats.  1 = supported (C a multiple of the 16-byte vector, <= 2048 channels).
+SG_EXPORT int sg_lrelu_bwd_bias_supported(int dtype, long long P, int C) {
+  const int VN = dtype == SG_BF16 ? 8 : 4;
+  if (C % VN != 0 || P < 1 || P >= (1ll << 31)) return 0;
+  const int CV = C / VN;
+  return CV <= 256 && (size_t)(256 / CV) * C * sizeof(float) <= 48 * 1024;
+}
+SG_EXPORT int sg_lrelu_bwd_bias(const void* g, const void* ref, void* gx, int dtype, long long P, int C, float* ws,
+                                float* gb, float scale, void* stream) {
+  SG_REQUIRE(sg_lrelu_bwd_bias_supported(dtype, P, C), "sg_lrelu_bwd_bias: shape not supported");
+  SG_REQUIRE(ws != nullptr && gb != nullptr, "sg_lrelu_bwd_bias: workspace / output missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = sg_channel_sum_blocks(P);
+  const int pix_per_blk = (int)((P + nblk - 1) / nblk);
+  SG_DISPATCH(dtype, {
+    const int CV = C / SgVec<T>::N;
+    const size_t smv = (size_t)(256 / CV) * C * sizeof(float);
+    lrelu_bwd_bias_kernel<T><<<nblk, 256, smv, st>>>((const T*)g, (const T*)ref, (T*)gx, P, C, ws, pix_per_blk);
+  });
+  int rc = sg_check_launch("sg_lrelu_bwd_bias");
+  if (rc) return rc;
+  partial_reduce_kernel<<<sg_cdiv(C, 4), 128, 0, st>>>(ws, nblk, C, gb, scale, 0);
+  return sg_check_launch("sg_lrelu_bwd_bias/reduce");
+}
+
 SG_EXPORT int sg_cast(const void* x, int dtype_in, void* y, int dtype_out, long long n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int grid = sg_grid_1d(n, 256, 148 * 32);
@@ -929,6 +1012,11 @@ SG_EXPORT int sg_channel_sum(const void* x, int dtype, const float* wt, int J, i
     // noise-weight + bias gradient: one per-pixel weight row plus the plain sum (same workspace layout and blocks)
     int rc = sgf_channel_sum_w1(x, wt, P, C, part_ws, out, scale, stream);
     if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_channel_sum/w1: launch failed"); return rc; }
+  }
+  if (g_sg_fast_paths && dtype == SG_BF16 && J == 3 && !accumulate) {
+    // rgb weight gradients: three per-pixel weight rows (+ the plain sum for from_rgb's bias)
+    int rc = sgf_channel_sum_w3(x, wt, ones, P, HW, C, part_ws, out, scale, stream);
+    if (rc != SG_FAST_UNSUPPORTED) { if (rc) sg_set_error("sg_channel_sum/w3: launch failed"); return rc; }
   }
   int nblk = sg_channel_sum_blocks(P);
   int pix_per_blk = (int)((P + nblk - 1) / nblk);

@@ -192,6 +192,76 @@ __global__ void __launch_bounds__(256) channel_sum_w1_kernel(const __nv_bfloat16
   }
 }
 
+// ---- the same with J = 3 per-pixel weight rows (+ the plain sum): the weight gradients of to_rgb (J = 3) and from_rgb
+//      (J = 3 + ones).  wt is [N][3][HW] float (an RGB image or its gradient), x NHWC bf16.
+//   part[blk][j][c] = sum_p wt[n(p)][j][hw(p)] * x[p][c]  (j < 3),  part[blk][3][c] = sum_p x[p][c] if ONES
+// The general channel_sum_vec_kernel spends 4 FMAs + index arithmetic per element whatever J is and ran at 1.9 TB/s.
+template <bool ONES>
+__global__ void __launch_bounds__(256) channel_sum_w3_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const float* __restrict__ wt, long long P, int HW, int C,
+                                                             float* __restrict__ part, int pix_per_blk) {
+  constexpr int VN = 8, U = 4, ROWS = ONES ? 4 : 3;
+  extern __shared__ float sm[];                            // [ROWS][PR][C]
+  const int CV = C / VN;
+  const int PR = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, pr = threadIdx.x / CV;
+  const long long p0 = (long long)blockIdx.x * pix_per_blk;
+  long long p1 = p0 + pix_per_blk;
+  if (p1 > P) p1 = P;
+  float acc[ROWS][VN];
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j)
+#pragma unroll
+    for (int k = 0; k < VN; ++k) acc[j][k] = 0.f;
+  if (pr < PR) {
+    auto unpack = [](const uint4& v, float (&f)[VN]) {
+      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < VN; ++e) f[e] = __uint_as_float((e & 1) ? (wd[e >> 1] & 0xffff0000u) : (wd[e >> 1] << 16));
+    };
+    for (long long pb = p0 + pr; pb < p1; pb += (long long)U * PR) {
+      uint4 v[U];
+      float wv[U][3];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {                        // U pixels in flight: one 16-byte x load + three weight loads each
+        const long long p = pb + (long long)u * PR;
+        if (p < p1) {
+          v[u] = *reinterpret_cast<const uint4*>(x + (size_t)p * C + cv * VN);
+          const unsigned n = (unsigned)p / (unsigned)HW;   // P < 2^31 (launcher)
+          const float* w = wt + (size_t)n * 3 * HW + ((unsigned)p - n * (unsigned)HW);
+          wv[u][0] = w[0]; wv[u][1] = w[HW]; wv[u][2] = w[2 * (size_t)HW];
+        } else {
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          wv[u][0] = wv[u][1] = wv[u][2] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float f[VN];
+        unpack(v[u], f);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+          acc[0][k] = fmaf(wv[u][0], f[k], acc[0][k]);
+          acc[1][k] = fmaf(wv[u][1], f[k], acc[1][k]);
+          acc[2][k] = fmaf(wv[u][2], f[k], acc[2][k]);
+          if (ONES) acc[3][k] += f[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) sm[((size_t)j * PR + pr) * C + cv * VN + k] = acc[j][k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ROWS * C; i += blockDim.x) {
+    const int j = i / C, c = i % C;
+    float s = 0.f;
+    for (int r = 0; r < PR; ++r) s += sm[((size_t)j * PR + r) * C + c];
+    part[((size_t)blockIdx.x * ROWS + j) * C + c] = s;
+  }
+}
+
 __global__ void __launch_bounds__(128) reduce_parts_kernel(const float* __restrict__ part, int nblk, int M,
                                                            float* __restrict__ out, float scale) {
   const int lane = threadIdx.x & 31;
@@ -244,6 +314,20 @@ SGN_EXPORT int sgf_channel_sum_blocks(long long P) {
   long long b = (P + 255) / 256;
   if (b > 148 * 4) b = 148 * 4;
   return b < 1 ? 1 : (int)b;
+}
+// J = 3 weight rows (+ ones): out[j][c] = scale * sum_p wt[n][j][hw] x[p][c]; ws: nblk*(3+ones)*C floats.
+SGN_EXPORT int sgf_channel_sum_w3(const void* x, const float* wt, int ones, long long P, int HW, int C, float* ws, float* out,
+                                  float scale, void* stream) {
+  const int CV = C / 8, rows = ones ? 4 : 3;
+  if (C % 8 != 0 || CV > 256 || (size_t)rows * (256 / CV) * C * sizeof(float) > 48 * 1024) return SG_FAST_UNSUPPORTED;
+  const int nblk = sgf_channel_sum_blocks(P);
+  const int ppb = (int)((P + nblk - 1) / nblk);
+  const size_t smem = (size_t)rows * (256 / CV) * C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ones) channel_sum_w3_kernel<true><<<nblk, 256, smem, st>>>((const __nv_bfloat16*)x, wt, P, HW, C, ws, ppb);
+  else channel_sum_w3_kernel<false><<<nblk, 256, smem, st>>>((const __nv_bfloat16*)x, wt, P, HW, C, ws, ppb);
+  reduce_parts_kernel<<<(rows * C + 3) / 4, 128, 0, st>>>(ws, nblk, rows * C, out, scale);
+  return (int)cudaGetLastError();
 }
 SGN_EXPORT int sgf_channel_sum_w1(const void* x, const float* wt, long long P, int C, float* ws, float* out, float scale,
                                   void* stream) {

@@ -92,7 +92,7 @@ class _Lib:
 
 
 # functions whose int return value is a result, not a status
-_PLAIN_INT = {"sg_fast_paths", "sg_pair_updown", "sg_abi_version", "sg_geom_size", "sg_entry_size", "sg_wgrad_splits", "sg_channel_sum_blocks",
+_PLAIN_INT = {"sg_lrelu_bwd_bias_supported", "sg_fast_paths", "sg_pair_updown", "sg_abi_version", "sg_geom_size", "sg_entry_size", "sg_wgrad_splits", "sg_channel_sum_blocks",
               "sg_chunk_elems", "sg_conv3x3_tc_supported", "sg_conv3x3_pair_supported", "sg_conv3x3_pair_slots", "sg_blur3_epi_slots", "sg_lingroup_rows", "sg_lingroup_supported", "sg_lingroup_fwd_blocks",
               "sg_lingroup_wgrad_blocks", "sg_wgrad3x3_tc_supported", "sg_wgrad3x3_tc_splits", "sg_wgrad3x3_v2_supported", "sg_wgrad3x3_v2_splits", "sg_convud_tc_supported", "sg_wgradud_tc_supported", "sg_wgradud_tc_splits"}
 

@@ -310,12 +310,16 @@ class ConvBiasAct(Function):
     def backward(ctx, gy):
         x, W, y = ctx.saved_tensors
         kind, scale, bias_mul, act, has_bias = ctx.cfg
-        g = LreluBwd.apply(gy, y) if act else gy
-        gx = Conv.apply(g, W, kind, "dgrad", scale) if ctx.needs_input_grad[0] else None
         wp = _want_params()
-        gW = ConvWgrad.apply(x, g, kind, scale, W.shape) if (ctx.needs_input_grad[1] and wp) else None
+        want_gb = has_bias and ctx.needs_input_grad[2] and wp
         gb = None
-        if has_bias and ctx.needs_input_grad[2] and wp:
+        if act and want_gb and LreluBwdBias.supported(gy):
+            g, gb = LreluBwdBias.apply(gy, y, bias_mul)             # one pass: masked gradient + its channel sums
+        else:
+            g = LreluBwd.apply(gy, y) if act else gy
+        gx = Conv.apply(g, W, kind, "dgrad", scale) if ctx.needs_input_grad[0] else None
+        gW = ConvWgrad.apply(x, g, kind, scale, W.shape) if (ctx.needs_input_grad[1] and wp) else None
+        if want_gb and gb is None:
             gb = ChannelSum.apply(g, None, True, bias_mul).reshape(-1)
         return gx, gW, gb, None, None, None, None
 
@@ -338,6 +342,37 @@ class LreluBwd(Function):
     def backward(ctx, gg):
         (ref,) = ctx.saved_tensors
         return LreluBwd.apply(gg, ref), None
+
+
+class LreluBwdBias(Function):
+    """(gx, gb) = (g * lrelu'(ref), bias_mul * sum over pixels of gx) in one pass over NHWC tensors; linear in g, gb is a
+    leaf gradient (not differentiable, like ChannelSum)."""
+
+    @staticmethod
+    def supported(g):
+        C = g.shape[-1]
+        return g.is_cuda and g.dim() == 4 and bool(lib.sg_lrelu_bwd_bias_supported(code(g.dtype), g.numel() // C, C))
+
+    @staticmethod
+    def forward(ctx, g, ref, bias_mul):
+        _require_cuda(g)
+        g, ref = _c(g), _c(ref)
+        assert g.dtype == ref.dtype and g.shape == ref.shape
+        C = g.shape[-1]
+        P = g.numel() // C
+        out = torch.empty_like(g)
+        gb = torch.empty((C,), dtype=torch.float32, device=g.device)
+        ws = torch.empty((lib.sg_channel_sum_blocks(P), C), dtype=torch.float32, device=g.device)
+        lib.sg_lrelu_bwd_bias(ptr(g), ptr(ref), ptr(out), code(g.dtype), P, C, ptr(ws), ptr(gb), float(bias_mul), stream())
+        count_launch(2)
+        ctx.save_for_backward(ref)
+        ctx.mark_non_differentiable(gb)
+        return out, gb
+
+    @staticmethod
+    def backward(ctx, gg, _):
+        (ref,) = ctx.saved_tensors
+        return LreluBwd.apply(gg, ref), None, None
 
 
 class ChannelSum(Function):

@@ -190,3 +190,54 @@ def test_wprep_fwd_bwd_match_einsum(co, ci, KK, npt, transpose):
         acc = base.clone()
         lib.sg_wprep_bwd(ptr(part), S, ptr(acc), co, ci, KK, npt, ptr(coef), scale, transpose, 1, _s())
         assert rel(acc, want + base.double()) < 1e-5
+
+
+@pytest.mark.parametrize("N,hw,C", [(2, 8, 16), (3, 31, 64), (1, 64, 128), (2, 16, 512), (2, 128, 64)])
+@pytest.mark.parametrize("ones", [0, 1])
+def test_channel_sum_three_weight_rows(N, hw, C, ones):
+    """rgb weight gradients (J = 3 per-pixel weight rows, + the plain sum for from_rgb's bias): csrc/sg_rgb_k3.cu
+    channel_sum_w3_kernel against the general kernel and torch."""
+    from models._lib import lib, ptr
+    torch.manual_seed(5)
+    P = N * hw * hw
+    rows = 3 + ones
+    x = torch.randn(N, hw, hw, C, device=DEV).to(torch.bfloat16)
+    wt = torch.randn(N, 3, hw, hw, device=DEV)
+
+    def run():
+        out = torch.full((rows, C), float("nan"), device=DEV)
+        ws = torch.empty(lib.sg_channel_sum_blocks(P) * rows * C, device=DEV)
+        lib.sg_channel_sum(ptr(x), 1, ptr(wt), 3, ones, P, hw * hw, C, ptr(ws), ptr(out), 0.5, 0, _s())
+        return out
+    fast, slow = both(run)
+    assert rel(fast, slow) < 1e-4
+    xf = x.float()
+    ref = [torch.einsum("nhw,nhwc->c", wt[:, j], xf) for j in range(3)]
+    if ones:
+        ref.append(xf.sum((0, 1, 2)))
+    assert rel(fast, torch.stack(ref) * 0.5) < 1e-4
+
+
+@pytest.mark.parametrize("N,hw,C", [(2, 8, 16), (3, 31, 64), (1, 64, 128), (2, 16, 512), (2, 128, 64)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_lrelu_bwd_bias_equals_two_passes(N, hw, C, dt):
+    """sg_lrelu_bwd_bias = sg_lrelu_bwd followed by the plain channel sum of its output (bitwise for gx; the sums are taken
+    over the rounded gx in both), and differentiable through LreluBwdBias exactly like LreluBwd."""
+    from models import _ops
+    from models._lib import lib, ptr, code
+    torch.manual_seed(7)
+    g = torch.randn(N, hw, hw, C, device=DEV).to(dt)
+    ref = torch.randn(N, hw, hw, C, device=DEV).to(dt)
+    P = N * hw * hw
+    assert lib.sg_lrelu_bwd_bias_supported(code(dt), P, C) == 1
+    want = torch.empty_like(g)
+    lib.sg_lrelu_bwd(ptr(g), ptr(ref), ptr(want), g.numel(), code(dt), _s())
+    gx, gb = _ops.LreluBwdBias.apply(g, ref, 0.7)
+    assert torch.equal(gx, want)
+    assert rel(gb, want.float().sum((0, 1, 2)) * 0.7) < 1e-5
+    gg = torch.randn_like(g).requires_grad_(True)
+    out, _ = _ops.LreluBwdBias.apply(gg, ref, 1.0)
+    (d,) = torch.autograd.grad(out, gg, g)
+    want2 = torch.empty_like(g)
+    lib.sg_lrelu_bwd(ptr(g), ptr(ref), ptr(want2), g.numel(), code(dt), _s())
+    assert torch.equal(d, want2)

@@ -67,6 +67,15 @@ int sg_lingroup_wgrad(const void* table, int G, int total_blocks, int B, int I, 
  * Replaces `self.weight * self.w_mul` (:171) and the 4x4 kernel merges (:146-150, :159-162). */
 int sg_wprep_fwd(const float* W, void* E, int dtype, int Cout, int Cin, int KK, int npt, const float* coef,
                  float scale, int transpose, void* stream);
+/* the same for many weights in one launch (bf16 outputs): one table row per weight */
+typedef struct SgWprepEntry {
+  long long W, E, coef;          /* device pointers: float32 parameter [Cout][Cin][KK], bf16 output, float32 coef [npt][KK] */
+  int Cout, Cin, KK, npt, transpose;
+  int tile0;                     /* first block of this row: running sum of ceil(Cout/32)*ceil(Cin/32) */
+  float scale;
+  int pad;
+} SgWprepEntry;
+int sg_wprep_fwd_multi(const void* table, int n, int total_tiles, int max_smem_floats, void* stream);
 /* dW = scale * coef^T . sum_splits(partial)  -- adjoint of sg_wprep_fwd applied to the wgrad partials. */
 int sg_wprep_bwd(const float* partial, int nsplit, float* dW, int Cout, int Cin, int KK, int npt, const float* coef,
                  float scale, int transpose, int accumulate, void* stream);

@@ -11,6 +11,7 @@
 //
 // This is the fp32 parity path and the universal fallback; the bf16 hot layers run sg_conv_tc.cu (tcgen05).
 #include "sg_common.cuh"
+#include <mutex>
 #include "../../include/sgb200.h"
 
 namespace {
@@ -246,16 +247,15 @@ __global__ void __launch_bounds__(NT) wgrad_generic_kernel(const T* __restrict__
 // global memory -- ran at a fifth of the copy bandwidth: 16 us for a 512x512x3x3 weight.)
 constexpr int WP_T = 32;
 template <class T>
-__global__ void __launch_bounds__(256) wprep_fwd_kernel(const float* __restrict__ W, T* __restrict__ E, int Cout, int Cin,
-                                                        int KK, int npt, const float* __restrict__ coef, float scale,
-                                                        int transpose) {
-  extern __shared__ float sm_w[];                   // [npt*KK coef][WP_T][WP_T*KK + 1]
-  float* s_coef = sm_w;
+__device__ __forceinline__ void wprep_fwd_tile(const float* __restrict__ W, T* __restrict__ E, int Cout, int Cin, int KK,
+                                               int npt, const float* __restrict__ coef, float scale, int transpose,
+                                               int tile, float* sm_w) {
+  float* s_coef = sm_w;                             // [npt*KK coef][WP_T][WP_T*KK + 1]
   float* s_w = sm_w + npt * KK;
   const int row = WP_T * KK + 1;
   for (int i = threadIdx.x; i < npt * KK; i += blockDim.x) s_coef[i] = coef[i];
   const int tiles_ci = (Cin + WP_T - 1) / WP_T;
-  const int co0 = (blockIdx.x / tiles_ci) * WP_T, ci0 = (blockIdx.x % tiles_ci) * WP_T;
+  const int co0 = (tile / tiles_ci) * WP_T, ci0 = (tile % tiles_ci) * WP_T;
   const int nci = min(WP_T, Cin - ci0), nco = min(WP_T, Cout - co0);
   {
     // 8 independent loads in flight per thread (one load per loop trip left every trip waiting for its own DRAM round
@@ -301,6 +301,27 @@ __global__ void __launch_bounds__(256) wprep_fwd_kernel(const float* __restrict_
       dst[(size_t)pt * AB] = sg_from_f<T>(acc);
     }
   }
+}
+template <class T>
+__global__ void __launch_bounds__(256) wprep_fwd_kernel(const float* __restrict__ W, T* __restrict__ E, int Cout, int Cin,
+                                                        int KK, int npt, const float* __restrict__ coef, float scale,
+                                                        int transpose) {
+  extern __shared__ float sm_w[];
+  wprep_fwd_tile<T>(W, E, Cout, Cin, KK, npt, coef, scale, transpose, blockIdx.x, sm_w);
+}
+// Many weights in ONE launch (the refresh of every derived bf16 copy after an optimizer step: 58 launches of 4-256 blocks
+// each, ~11 us apiece, were 0.7 ms of a 30 ms step): block -> table row by binary search on the first tile of each row.
+__global__ void __launch_bounds__(256) wprep_fwd_multi_kernel(const SgWprepEntry* __restrict__ tab, int n) {
+  extern __shared__ float sm_w[];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const SgWprepEntry e = tab[lo];
+  wprep_fwd_tile<__nv_bfloat16>(reinterpret_cast<const float*>(e.W), reinterpret_cast<__nv_bfloat16*>(e.E), e.Cout, e.Cin,
+                                e.KK, e.npt, reinterpret_cast<const float*>(e.coef), e.scale, e.transpose,
+                                (int)blockIdx.x - e.tile0, sm_w);
 }
 
 // dW[co][ci][j] (+)= scale * sum_{pt} coef[pt][j] * sum_s partial[s][pt][a][b]
@@ -472,6 +493,21 @@ SG_EXPORT int sg_wprep_fwd(const float* W, void* E, int dtype, int Cout, int Cin
     wprep_fwd_kernel<T><<<tiles, 256, smem, st>>>(W, (T*)E, Cout, Cin, KK, npt, coef, scale, transpose);
   });
   return sg_check_launch("sg_wprep_fwd");
+}
+
+// table: n rows of SgWprepEntry in device memory (bf16 outputs; tile0 = running sum of ceil(Cout/32)*ceil(Cin/32));
+// total_tiles = the sum over all rows; max_smem_floats = max over rows of npt*KK + 32*(32*KK + 1).
+SG_EXPORT int sg_wprep_fwd_multi(const void* table, int n, int total_tiles, int max_smem_floats, void* stream) {
+  if (n <= 0 || total_tiles <= 0) return 0;
+  SG_REQUIRE(table != nullptr && max_smem_floats > 0 && (size_t)max_smem_floats * sizeof(float) <= 96 * 1024,
+             "sg_wprep_fwd_multi: bad arguments");
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(wprep_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  });
+  wprep_fwd_multi_kernel<<<total_tiles, 256, (size_t)max_smem_floats * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const SgWprepEntry*>(table), n);
+  return sg_check_launch("sg_wprep_fwd_multi");
 }
 
 SG_EXPORT int sg_wprep_bwd(const float* partial, int nsplit, float* dW, int Cout, int Cin, int KK, int npt,

@@ -161,8 +161,11 @@ def cached_weight(W, sub, build):
     tok = _token_of(W)
     it = ent[1].get(sub)
     if it is None:
+        _last_wprep[0] = None
         E = build(W, None)
-        ent[1][sub] = [E, build, tok]
+        rec = _last_wprep[0]                 # the build was one sg_wprep_fwd into E: remember its arguments (batched refresh)
+        desc = rec[1] if (rec is not None and isinstance(E, torch.Tensor) and rec[0] == E.data_ptr()) else None
+        ent[1][sub] = [E, build, tok, desc]
         return E
     if it[2] != tok:
         build(W, it[0])
@@ -170,9 +173,50 @@ def cached_weight(W, sub, build):
     return it[0]
 
 
+_last_wprep = [None]
+_wprep_tables = {}
+
+
+def wprep_fwd(W, E, dtype, co, ci, KK, npt, coef, scale, transpose):
+    """sg_wprep_fwd, recording its arguments for cached_weight (refresh_derived re-issues all recorded bf16 preparations
+    of an optimizer's parameters as ONE sg_wprep_fwd_multi launch)."""
+    Wc = _c(W.detach())
+    lib.sg_wprep_fwd(ptr(Wc), ptr(E), code(dtype), co, ci, KK, npt, ptr(coef), float(scale), int(transpose), stream())
+    count_launch()
+    if dtype == torch.bfloat16 and Wc.data_ptr() == W.data_ptr() and W.dtype == torch.float32:
+        _last_wprep[0] = (E.data_ptr(), (W.data_ptr(), E.data_ptr(), coef.data_ptr(), int(co), int(ci), int(KK), int(npt),
+                                         int(transpose), float(scale), coef))
+    else:
+        _last_wprep[0] = None
+
+
+def _wprep_multi(descs, device):
+    """One launch for a list of recorded sg_wprep_fwd calls; the device table is cached per exact list."""
+    import numpy as np
+    key = tuple(d[:9] for d in descs)
+    ent = _wprep_tables.get(key)
+    if ent is None:
+        rows = np.zeros(len(descs), dtype=np.dtype([("W", "<i8"), ("E", "<i8"), ("coef", "<i8"), ("Cout", "<i4"),
+                                                    ("Cin", "<i4"), ("KK", "<i4"), ("npt", "<i4"), ("transpose", "<i4"),
+                                                    ("tile0", "<i4"), ("scale", "<f4"), ("pad", "<i4")]))
+        assert rows.dtype.itemsize == 56
+        tile0, smem = 0, 0
+        for i, (Wp, Ep, Cp, co, ci, KK, npt, tr, scale, _coef) in enumerate(descs):
+            rows[i] = (Wp, Ep, Cp, co, ci, KK, npt, tr, tile0, scale, 0)
+            tile0 += ((co + 31) // 32) * ((ci + 31) // 32)
+            smem = max(smem, npt * KK + 32 * (32 * KK + 1))
+        t = torch.from_numpy(rows.view(np.uint8).copy())
+        if len(_wprep_tables) > 64:
+            _wprep_tables.clear()
+        ent = _wprep_tables[key] = (upload_table(t, device), tile0, smem)
+    lib.sg_wprep_fwd_multi(ptr(ent[0]), len(descs), ent[1], ent[2], stream())
+    count_launch()
+
+
 def refresh_derived(params):
     """Rebuild, in place, every cached variant of the given parameters (called by the optimizer right after it has
     rewritten them and bumped their update counter)."""
+    batch, dev = [], None
     for W in params:
         ent = _prep_cache.get(id(W))
         if ent is None or ent[2]() is not W:
@@ -182,8 +226,14 @@ def refresh_derived(params):
             continue
         tok = _token_of(W)
         for it in ent[1].values():
-            it[1](W, it[0])
+            if it[3] is not None and it[3][0] == W.data_ptr() and it[3][1] == it[0].data_ptr():
+                batch.append(it[3])                     # a plain sg_wprep_fwd into a bf16 buffer: goes into the one launch
+            else:
+                it[1](W, it[0])
             it[2] = tok
+            dev = W.device
+    if batch:
+        _wprep_multi(batch, dev)
 
 
 def prepped_weight(W, kind, direction, dtype, scale):
@@ -195,9 +245,7 @@ def prepped_weight(W, kind, direction, dtype, scale):
         a, b = (co, ci) if t["transpose"] else (ci, co)
         E = out if out is not None else torch.empty((npt, a, b), dtype=dtype, device=W.device)
         coef = _coef_dev(kind, k, direction, W.device)
-        lib.sg_wprep_fwd(ptr(_c(W.detach())), ptr(E), code(dtype), co, ci, k * k, npt, ptr(coef), float(scale),
-                         t["transpose"], stream())
-        count_launch()
+        wprep_fwd(W, E, dtype, co, ci, k * k, npt, coef, scale, t["transpose"])
         return E
     return cached_weight(W, (kind, direction, dtype, float(scale)), build)
 
@@ -212,6 +260,7 @@ def bump_weights_epoch():
 
 def clear_weight_cache():
     _prep_cache.clear()
+    _wprep_tables.clear()
 
 
 # ---------------------------------------------------------------------------------------------------------------

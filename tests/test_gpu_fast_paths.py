@@ -265,7 +265,7 @@ def test_batched_weight_refresh_equals_individual_builds():
     ptrs = [[e.data_ptr() for e in v] for v in before]
     with torch.no_grad():
         for W in Ws:
-            W.add_(torch.randn_like(W))                  # rewritten "behind autograd's back", as the fused optimizer does
+            W.data.add_(torch.randn_like(W))             # rewritten behind autograd's back (no _version bump), as the fused optimizer does
     tok[0] += 1
     l0 = launches()
     _ops.refresh_derived(Ws)
@@ -279,4 +279,3 @@ def test_batched_weight_refresh_equals_individual_builds():
     for a, b in zip(refreshed, fresh):
         for x, y in zip(a, b):
             assert torch.equal(x, y)
-    assert not torch.equal(refreshed[0][0], before[0][0]) or True

@@ -17,6 +17,7 @@ step to step through device memory instead of kernel arguments:
 TMA descriptors are encoded on the host at capture time; they stay valid because all activations of a captured step
 live in the graph's private memory pool, which replays the same addresses."""
 import random
+import os
 import warnings
 
 import torch
@@ -110,8 +111,11 @@ class StepGraphs:
             except Exception as ex:                     # stay correct: fall back to the eager path for this key
                 e.failed, e.graph = True, None
                 _ops._capture[0] = None
-                warnings.warn("sgb200: CUDA-graph capture of the %s step failed (%s: %s); running it eagerly"
-                              % (kind, type(ex).__name__, str(ex)[:200]))
+                import traceback
+                where = " <- ".join("%s:%d %s" % (os.path.basename(f.filename), f.lineno, f.name)
+                                    for f in traceback.extract_tb(ex.__traceback__)[-6:])
+                warnings.warn("sgb200: CUDA-graph capture of the %s step failed (%s: %s) at %s; running it eagerly"
+                              % (kind, type(ex).__name__, str(ex)[:200], where))
                 return body(noise, real, depth, alpha, labels)
         return self._replay(e, noise, real, depth, alpha)
 

@@ -121,6 +121,7 @@ def test_nccl_data_parallel_world2():
         if p.exitcode is None:
             p.kill()
         assert p.exitcode == 0
+    print("per-rank (rank, err, differ, same, finite, captured):", res)
     for rank, err, differ, same, finite, captured in res:
         assert err < 1e-5, (rank, err)                # NCCL sum * 1/world == mean of the ranks' gradients
         assert differ                                 # the ranks did not all compute the same gradient

@@ -68,6 +68,9 @@ def _worker(rank, world, port, q):
         got = torch.cat([p.grad.detach().reshape(-1).double() for p in params]) * scale
         err = float((got - mean).norm() / (mean.norm() + 1e-30))
         sg.dis_optim.zero_grad()
+        # drop every reference to the autograd graph of the eager check above: its AccumulateGrad nodes were created on the
+        # default stream, and a kept-alive one would run there during the capture (on a side stream) and invalidate it
+        del loss, fake, local, gathered, mean, got, params
         losses = []
         for i in range(5):                            # steps 0-1 eager, step 2 captures, 3-4 replay
             img = torch.randn(B, 3, R, R, device=dev)

@@ -218,8 +218,11 @@ def northstar_traffic(batch, res, ch, kernel=""):
     return {"traffic": None, "traffic_unit": "bytes/launch", "traffic_source": None}
 
 
-def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):
-    """Times the oracle port of the reference's G+D step on the host cores.  -> (seconds/step list, threads)."""
+def cpu_oracle_step_time(res, batch, steps, warmup, threads=None, budget_s=None):
+    """Times the oracle port of the reference's G+D step on the host cores.  -> (seconds/step list, threads).
+    budget_s bounds the leg on a slow or shared host (a 256x256 step took 12 s on one box and 60-128 s on another): once
+    the elapsed time (warm-up included) exceeds it, the loop stops after the current step -- at least one timed step is
+    always taken, and the caller reports how many were."""
     import random
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -232,7 +235,10 @@ def cpu_oracle_step_time(res, batch, steps, warmup, threads=None):
     st = O.TrainState(arch, O.init_generator(arch, gen), O.init_discriminator(arch, gen))
     depth = arch.depth - 1
     times = []
+    t_begin = time.perf_counter()
     for i in range(warmup + steps):
+        if budget_s is not None and times and time.perf_counter() - t_begin > budget_s:
+            break
         real = torch.randn(batch, 3, res, res)
         z = torch.randn(batch, 512)
         noises_d = [torch.randn(s) for s in O.noise_shapes(arch, batch, depth)]
@@ -365,9 +371,11 @@ def run_reference(args, rank, world):
     # absorb); the JSON line reports the warm-up actually run
     batch = args.ref_batch if args.steps + args.warmup <= 4 else 1
     args.warmup = min(args.warmup, 1)
-    times, threads = cpu_oracle_step_time(args.res, batch, args.steps, args.warmup)
+    times, threads = cpu_oracle_step_time(args.res, batch, args.steps, args.warmup,
+                                          budget_s=float(os.environ.get("SG_REFERENCE_BUDGET_S", "180")))
     sec = sum(times) / len(times)
     val = batch / sec
+    steps_requested, args.steps = args.steps, len(times)   # a slow host stops early (budget): report the steps really timed
     out = {"impl": "reference", "metric": "images/sec G+D step @%dx%d bs=%d/GPU" % (args.res, args.res, args.batch),
            "value": round(val, 4),
            "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -376,9 +384,10 @@ def run_reference(args, rank, world):
            "config": {"workload": "G+D step (logistic+R1, EMA) %dx%d depth %d" % (args.res, args.res, O_depth(args.res)),
                       "batch_per_step": batch, "device": "host CPU"},
            "cpu_baseline": {"value": round(val, 4), "unit": "images/sec", "cores": threads, "kind": "port",
-                            "sample": "%d timed G+D steps at batch %d (the reference is Python and absent on the GPU "
-                                      "box; this is oracle/stylegan_oracle.py, pinned to it in the build container)"
-                                      % (args.steps, batch)},
+                            "sample": "%d timed G+D steps (of %d requested; time budget %s s) at batch %d (the reference is "
+                                      "Python and absent on the GPU box; this is oracle/stylegan_oracle.py, pinned to it in "
+                                      "the build container)"
+                                      % (args.steps, steps_requested, os.environ.get("SG_REFERENCE_BUDGET_S", "180"), batch)},
            "e2e": {"value": round(val, 4), "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -554,11 +563,11 @@ def main():
             out["gpu_baseline"] = gb
         if world == 1 and not args.no_cpu_baseline:
             cb = 1                                          # ~10 s of CPU per image at 256x256: 1 warm-up + 3 timed steps
-            t, threads = cpu_oracle_step_time(R, cb, 3, 1)
+            t, threads = cpu_oracle_step_time(R, cb, 3, 1, budget_s=45.0)
             out["cpu_baseline"] = {"value": round(cb * len(t) / sum(t), 4), "unit": "images/sec", "cores": threads,
-                                   "kind": "port", "sample": "1 warm-up + 3 timed G+D steps at %dx%d, batch %d (the "
-                                   "per-image cost of this path does not depend on the batch), oracle port on the "
-                                   "host CPU, all %d threads" % (R, R, cb, threads),
+                                   "kind": "port", "sample": "1 warm-up + %d timed G+D steps (3 unless the 45 s budget of this leg ran out) at "
+                                   "%dx%d, batch %d (the per-image cost of this path does not depend on the batch), oracle "
+                                   "port on the host CPU, all %d threads" % (len(t), R, R, cb, threads),
                                    "sec_per_step": [round(x, 2) for x in t]}
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -14,9 +14,10 @@
 // cta_group::2 form (M = 256: 128 pixels from each CTA, each CTA holding N/2 rows of the weights) measured 43 cycles at
 // N = 64 and 64 at N = 128 (profiles/r02_mma_rate2.txt: 1573 / 2046 TFLOP/s chip-wide with operands resident).
 //
-// Structure per CTA (both CTAs of the cluster): warp 0 TMA producer (own activation halo box + own half of the weights,
-// completion signalled on the LEADER's mbarrier via the cta_group::2 TMA form), warp 1 MMA issuer (leader CTA only),
-// warps 2-9 epilogue of the CTA's own 128-pixel tile.  A pair walks a CONTIGUOUS range of tile pairs, so the per-image
+// Structure per CTA (both CTAs of the cluster): warp 0 TMA producer (own 18x10 activation halo box per 64-channel chunk
+// + own half of the weights, completion signalled on the LEADER's mbarrier via the cta_group::2 TMA form), warps 1 and 10
+// MMA issuers (leader CTA only; alternate tiles -- one warp cannot issue tcgen05.mma fast enough, see below), warps 2-9
+// two epilogue teams for the CTA's own 128-pixel (16 x 8) tiles.  A pair walks a CONTIGUOUS range of tile pairs, so the per-image
 // statistics are accumulated in registers across tiles and flushed once per (CTA, image): deterministic two-stage
 // reduction, no atomics (sg_epi_finalize_parts sums the slots in fixed order).
 #include "sg_common.cuh"

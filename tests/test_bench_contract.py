@@ -44,3 +44,16 @@ def test_product_arm_needs_cuda():
         return
     r = _run("--steps", "1", "--warmup", "0")
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_time_budget_stops_early_and_says_so():
+    """On a slow or shared host the CPU arm stops after the step that exhausts its time budget (at least one timed step)
+    and reports the number of steps it really timed."""
+    r = _run("--impl", "reference", "--steps", "6", "--warmup", "1", "--res", "16", env={"SG_REFERENCE_BUDGET_S": "0.0001"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0
+    assert "of 6 requested" in d["cpu_baseline"]["sample"]
+    r = _run("--impl", "reference", "--steps", "3", "--warmup", "1", "--res", "16", env={"SG_REFERENCE_BUDGET_S": "600"})
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["steps"] == 3

@@ -150,3 +150,41 @@ def test_weight_cache_is_keyed_on_the_parameter_object():
     _ops.refresh_derived([W])
     assert float(b[0]) == 9.0
     assert _ops.cached_weight(W, "k", lambda W, out: (_ for _ in ()).throw(AssertionError("current: no rebuild"))) is b
+
+
+def test_refresh_derived_batches_recorded_weight_preparations(monkeypatch):
+    """refresh_derived sends every variant that was built by one recorded sg_wprep_fwd into a bf16 buffer to ONE
+    sg_wprep_fwd_multi launch and rebuilds the others through their build closures (host logic; the kernel itself is
+    tested on the GPU: tests/test_gpu_fast_paths.py)."""
+    from models import _ops
+    _ops.clear_weight_cache()
+    W1 = torch.nn.Parameter(torch.zeros(4, 4, 3, 3))
+    W2 = torch.nn.Parameter(torch.zeros(2, 2))
+    tok = [0]
+    W1._sg_token = W2._sg_token = tok
+    coef = torch.zeros(9, 9)
+    rebuilt = []
+
+    def recorded_build(W, out):                       # what _ops.wprep_fwd leaves behind for cached_weight
+        E = out if out is not None else torch.zeros(9, 4, 4, dtype=torch.bfloat16)
+        rebuilt.append("recorded")
+        _ops._last_wprep[0] = (E.data_ptr(), (W.data_ptr(), E.data_ptr(), coef.data_ptr(), 4, 4, 9, 9, 1, 0.5, coef))
+        return E
+
+    def plain_build(W, out):
+        rebuilt.append("plain")
+        return out if out is not None else W.detach().clone()
+
+    E1 = _ops.cached_weight(W1, "tc", recorded_build)
+    E2 = _ops.cached_weight(W2, "other", plain_build)
+    assert rebuilt == ["recorded", "plain"]
+    batches = []
+    monkeypatch.setattr(_ops, "_wprep_multi", lambda descs, dev: batches.append([d[:9] for d in descs]))
+    tok[0] += 1
+    _ops.refresh_derived([W1, W2])
+    assert rebuilt == ["recorded", "plain", "plain"]   # W2's variant through its closure, W1's through the batch
+    assert batches == [[(W1.data_ptr(), E1.data_ptr(), coef.data_ptr(), 4, 4, 9, 9, 1, 0.5)]]
+    # both are current now: no rebuild on use
+    boom = lambda W, out: (_ for _ in ()).throw(AssertionError("current: no rebuild"))
+    assert _ops.cached_weight(W1, "tc", boom) is E1 and _ops.cached_weight(W2, "other", boom) is E2
+    _ops.clear_weight_cache()
